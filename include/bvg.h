@@ -1,0 +1,173 @@
+/*
+ * bvg.h — C ABI of libbvg.so, the B200-native (sm_100a) BigVGAN waveform decoder.
+ *
+ * Drop-in boundary for ONE path of CreateIntelligens/index-tts-lora:
+ *     wav, _ = self.bigvgan(latent, cond_input)          indextts/infer.py:748, :888
+ * i.e. indextts/BigVGAN/models.py:203-252 (BigVGAN.forward) minus the ECAPA speaker
+ * encoder (models.py:204), which stays in PyTorch on the host side.
+ *
+ * Conventions (all entry points):
+ *   - plain C, no torch / pybind types; loaded with ctypes;
+ *   - returns 0 on success, a negative bvg_status otherwise; never throws, never falls
+ *     back to another backend or to the CPU.  bvg_last_error() gives the message
+ *     (thread-local);
+ *   - the CALLER owns every tensor it passes; a plan owns only its packed weights and its
+ *     grow-only activation workspace;
+ *   - all device work is enqueued on the caller's stream (`stream` is a cudaStream_t passed
+ *     as void*; NULL = legacy default stream); no internal synchronisation except where a
+ *     function says so (`*_host` variants and bvg_plan_load_weights);
+ *   - one plan per (device, config); plans are independent, so 8 plans can be driven from
+ *     8 host threads or from one thread round-robin;
+ *   - requires compute capability 10.x (B200); anything else → BVG_ERR_ARCH.
+ *
+ * Tensor layouts are the reference's: activations [B, C, T] channel-major contiguous,
+ * latents [B, T, gpt_dim] time-major (models.py:215-222 transposes; we consume time-major
+ * directly), Conv1d weights [C_out, C_in, k], ConvTranspose1d weights [C_in, C_out, k].
+ */
+#ifndef BVG_H_
+#define BVG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BVG_VERSION 100 /* major*10000 + minor*100 + patch */
+
+typedef enum bvg_status {
+  BVG_OK = 0,
+  BVG_ERR_ARG = -1,     /* bad argument / shape / missing tensor */
+  BVG_ERR_CUDA = -2,    /* a CUDA runtime call failed */
+  BVG_ERR_ARCH = -3,    /* device is not sm_100 */
+  BVG_ERR_STATE = -4,   /* plan has no weights loaded, etc. */
+  BVG_ERR_UNSUPPORTED = -5
+} bvg_status;
+
+typedef enum bvg_dtype { BVG_F32 = 0, BVG_BF16 = 1, BVG_F16 = 2, BVG_I16 = 3 } bvg_dtype;
+
+/* Arithmetic path.  BVG_PREC_F32: SIMT FFMA everywhere (the 1e-4 exactness path).
+ * BVG_PREC_BF16: bf16 operands on tcgen05/TMEM tensor cores, fp32 accumulation, fp32
+ * FIR/snake math (the throughput path; waveform SNR >= 40 dB vs the fp32 reference). */
+typedef enum bvg_precision { BVG_PREC_F32 = 0, BVG_PREC_BF16 = 1 } bvg_precision;
+
+#define BVG_MAX_UPS 8
+#define BVG_MAX_KERNELS 4
+#define BVG_MAX_DIL 3
+
+/* Mirrors the `bigvgan:` block of finetune_models/config.yaml:88-146 — only the keys
+ * BigVGAN.__init__ reads (models.py:144-199). */
+typedef struct bvg_config {
+  int32_t gpt_dim;                  /* 1280  (conv_pre input channels, models.py:151) */
+  int32_t upsample_initial_channel; /* 1536 */
+  int32_t num_upsamples;            /* 6 */
+  int32_t upsample_rates[BVG_MAX_UPS];        /* 4,4,4,4,2,2 */
+  int32_t upsample_kernel_sizes[BVG_MAX_UPS]; /* 8,8,4,4,4,4 */
+  int32_t num_kernels;              /* 3 */
+  int32_t resblock_kernel_sizes[BVG_MAX_KERNELS];             /* 3,7,11 */
+  int32_t resblock_dilation_sizes[BVG_MAX_KERNELS][BVG_MAX_DIL]; /* 1,3,5 each */
+  int32_t speaker_embedding_dim;    /* 512 */
+  int32_t cond_in_each_up_layer;    /* 1 */
+  int32_t snake_logscale;           /* 1 */
+} bvg_config;
+
+/* A named tensor in the reference's state-dict naming AFTER weight-norm folding
+ * (models.py:254-262): "conv_pre.weight", "ups.0.0.weight", "resblocks.3.convs1.0.bias",
+ * "resblocks.3.activations.0.act.alpha", "...upsample.filter",
+ * "...downsample.lowpass.filter", "activation_post.act.beta", "conv_post.weight",
+ * "cond_layer.weight", "conds.2.bias", ...  `data` is a DEVICE pointer, fp32, contiguous. */
+typedef struct bvg_tensor_desc {
+  const char* name;
+  const void* data;
+  int32_t dtype; /* bvg_dtype; only BVG_F32 accepted */
+  int32_t ndim;
+  int64_t shape[4];
+} bvg_tensor_desc;
+
+typedef struct bvg_plan bvg_plan;
+
+int bvg_version(void);
+const char* bvg_last_error(void);
+
+/* Replaces BigVGAN.__init__ (models.py:132-199) for the generator half. */
+int bvg_plan_create(const bvg_config* cfg, int device, bvg_plan** out);
+int bvg_plan_destroy(bvg_plan* plan);
+
+/* Replaces load_state_dict + remove_weight_norm + dtype cast (infer.py:392-409): copies and
+ * re-packs the folded fp32 weights into the plan's own buffers (fp32 tap-major for the SIMT
+ * path, bf16 UMMA core-matrix tiles for the tcgen05 path) and precomputes exp(alpha),
+ * 1/(exp(beta)+1e-9).  Synchronises `stream` before returning (the caller may free its
+ * tensors afterwards). */
+int bvg_plan_load_weights(bvg_plan* plan, const bvg_tensor_desc* tensors, int n, void* stream);
+
+/* Replaces BigVGAN.forward (models.py:212-252) after the speaker encoder.
+ *   latent   device, [B, Tmax, gpt_dim], dtype latent_dtype (F32 / BF16 / F16)
+ *   lengths  HOST int32[B], valid latent frames per utterance (NULL = all Tmax).  Each
+ *            utterance is decoded with true sequence-edge rules at ITS length, so a ragged
+ *            batch equals per-utterance reference runs (the reference has no masking).
+ *   spk_emb  device fp32 [B, speaker_embedding_dim] — ECAPA output (models.py:204,212)
+ *   wav_out  device, [B, 1, Tmax * prod(upsample_rates)], dtype wav_dtype:
+ *            F32/BF16/F16 = tanh output (models.py:250);  I16 = clamp(32767*wav) as in
+ *            infer.py:892.  Samples beyond an utterance's length are written as 0.
+ */
+int bvg_decode(bvg_plan* plan, const void* latent, int latent_dtype, const int32_t* lengths,
+               int B, int Tmax, const float* spk_emb, void* wav_out, int wav_dtype,
+               int precision, void* stream);
+
+/* Same, with HOST buffers (pinned for async copies): H2D of latent + spk_emb, decode, D2H of
+ * wav, then synchronises `stream`.  This is the end-to-end call bench.py times as `e2e`. */
+int bvg_decode_host(bvg_plan* plan, const void* latent_host, int latent_dtype,
+                    const int32_t* lengths, int B, int Tmax, const float* spk_emb_host,
+                    void* wav_out_host, int wav_dtype, int precision, void* stream);
+
+/* Time-split decode of one long utterance shard (BASELINE config 5): decodes latent frames
+ * [f_begin, f_end) of an utterance of f_total frames given the shard's latent WITH
+ * `halo_l`/`halo_r` extra frames actually present on each side (overlap-recompute: the halos
+ * are consumed, true-edge rules apply only where the shard touches frame 0 / f_total).
+ *   latent   device [halo_l + (f_end-f_begin) + halo_r, gpt_dim]
+ *   wav_out  device [(f_end-f_begin) * prod(upsample_rates)]
+ */
+int bvg_decode_shard(bvg_plan* plan, const void* latent, int latent_dtype, int f_begin,
+                     int f_end, int f_total, int halo_l, int halo_r, const float* spk_emb,
+                     void* wav_out, int wav_dtype, int precision, void* stream);
+
+/* Number of latent frames of context each side that makes bvg_decode_shard exact
+ * (receptive field of the generator in latent frames, rounded up). */
+int bvg_receptive_field_frames(const bvg_plan* plan);
+
+/* Bytes of workspace currently held / kernels launched by the last decode (for bench.py's
+ * gpu_launches). */
+int64_t bvg_plan_workspace_bytes(const bvg_plan* plan);
+int bvg_plan_last_launches(const bvg_plan* plan);
+
+/* ---- per-op entry points (tests, and the reference's own native-op boundary) ---------- */
+
+/* Supersedes anti_alias_activation_cuda.forward(input, up_filter, down_filter, alpha, beta)
+ * (alias_free_activation/cuda/anti_alias_activation.cpp:19-23, .cu:214-256) with the exact
+ * edge semantics of the torch Activation1d (alias_free_torch/act.py:24-29).
+ *   x, y [B, C, T] contiguous, dtype F32/BF16/F16;  up/down filter fp32[12]; alpha, beta
+ *   fp32[C] device;  logscale: 1 = parameters are log-scale (exp applied inside). */
+int bvg_activation1d(const void* x, void* y, int dtype, int B, int C, int T,
+                     const float* up_filter, const float* down_filter, const float* alpha,
+                     const float* beta, int logscale, void* stream);
+
+/* One fused AMPBlock1 layer (models.py:65-74, one `xt = conv(act(x))` step):
+ *   y = [acc +] conv1d(act1d(x); w, bias, dilation, padding=(k-1)*d/2) [+ resid]
+ * x, y, resid [B, C, T] fp32;  w [C_out=C, C_in=C, k] fp32; precision selects the SIMT or the
+ * tcgen05 path (the latter rounds operands to bf16).  act==0 skips the activation (plain
+ * Conv1d, used for conv_pre-like layers). */
+int bvg_amp_layer(const float* x, float* y, const float* resid, int B, int C_in, int C_out,
+                  int T, const float* w, const float* bias, int k, int dilation, int act,
+                  const float* up_filter, const float* down_filter, const float* alpha,
+                  const float* beta, int logscale, int precision, void* stream);
+
+/* ConvTranspose1d(C_in, C_out, k, stride=u, padding=(k-u)/2) (models.py:157-163), fp32
+ * [B,C_in,T] -> [B,C_out,T*u];  w [C_in, C_out, k]. */
+int bvg_conv_transpose1d(const float* x, float* y, int B, int C_in, int C_out, int T,
+                         const float* w, const float* bias, int k, int u, int precision,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BVG_H_ */

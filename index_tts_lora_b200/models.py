@@ -1,0 +1,406 @@
+"""Drop-in replacement for ``indextts.BigVGAN.models.BigVGAN`` (the generator half).
+
+Mirrors the reference interface for the ONE path ``wav, _ = self.bigvgan(latent, mel_ref)``
+(``indextts/infer.py:748,888``):
+
+* ``BigVGAN(h, use_cuda_kernel=False)``            — models.py:132-199 (writes ``h["use_cuda_kernel"]``)
+* ``forward(x, mel_ref, lens=None) -> (wav, None)`` — models.py:203-252
+* ``remove_weight_norm()``                          — models.py:254-262
+* ``state_dict`` keys/shapes identical to ``bigvgan_generator.pth["generator"]`` in both the
+  ``weight_g/weight_v`` and the folded ``weight`` form, including the 12-tap filter buffers and
+  ``speaker_encoder.*``; ``.to()``, ``.half()``, ``.to(torch.bfloat16)``, ``.modules()``, ``.eval()``
+  behave as for any ``nn.Module`` (infer.py:392-410).
+
+The torch modules below only HOLD parameters.  All generator arithmetic runs in libbvg.so
+(hand-written sm_100a CUDA behind the C ABI of include/bvg.h); the ECAPA speaker encoder stays
+PyTorch.  There is no torch/CPU fallback: without a B200 and a built libbvg.so, forward raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence
+
+import torch
+import torch.nn as nn
+from torch.nn import Conv1d, ConvTranspose1d
+from torch.nn.utils import remove_weight_norm, weight_norm
+
+from . import _lib
+from .ecapa import ECAPA_TDNN
+
+
+def get_padding(kernel_size: int, dilation: int = 1) -> int:
+    """utils.py:59-60"""
+    return (kernel_size * dilation - dilation) // 2
+
+
+def init_weights(m, mean: float = 0.0, std: float = 0.01) -> None:
+    """utils.py:47-50 — N(mean, std) on every Conv* weight."""
+    if m.__class__.__name__.find("Conv") != -1:
+        m.weight.data.normal_(mean, std)
+
+
+def kaiser_sinc_filter1d(cutoff: float, half_width: float, kernel_size: int) -> torch.Tensor:
+    """Tap generator of alias_free_torch/filter.py:29-58, returns [1,1,kernel_size]."""
+    import math
+
+    half = kernel_size // 2
+    a = 2.285 * (half - 1) * math.pi * 4 * half_width + 7.95
+    beta = 0.1102 * (a - 8.7) if a > 50.0 else (
+        0.5842 * (a - 21.0) ** 0.4 + 0.07886 * (a - 21.0) if a >= 21.0 else 0.0)
+    window = torch.kaiser_window(kernel_size, beta=beta, periodic=False)
+    if kernel_size % 2 == 0:
+        time = torch.arange(-half, half) + 0.5
+    else:
+        time = torch.arange(kernel_size) - half
+    if cutoff == 0:
+        filt = torch.zeros_like(time)
+    else:
+        filt = 2 * cutoff * window * torch.sinc(2 * cutoff * time)
+        filt = filt / filt.sum()
+    return filt.view(1, 1, kernel_size)
+
+
+# ------------------------------------------------------------------ parameter containers
+class SnakeBeta(nn.Module):
+    """activations.py:63-122 — holds per-channel alpha / beta (log-scale when configured)."""
+
+    def __init__(self, in_features, alpha=1.0, alpha_trainable=True, alpha_logscale=False):
+        super().__init__()
+        self.in_features = in_features
+        self.alpha_logscale = alpha_logscale
+        init = torch.zeros(in_features) if alpha_logscale else torch.ones(in_features)
+        self.alpha = nn.Parameter(init * alpha, requires_grad=alpha_trainable)
+        self.beta = nn.Parameter(init.clone() * alpha, requires_grad=alpha_trainable)
+        self.no_div_by_zero = 1e-9
+
+
+class _Filter(nn.Module):
+    def __init__(self, ratio, kernel_size):
+        super().__init__()
+        self.register_buffer("filter", kaiser_sinc_filter1d(0.5 / ratio, 0.6 / ratio, kernel_size))
+
+
+class UpSample1d(_Filter):
+    """resample.py:10-33 (buffer ``filter``)."""
+
+    def __init__(self, ratio=2, kernel_size=12):
+        super().__init__(ratio, kernel_size)
+        self.ratio = ratio
+
+
+class DownSample1d(nn.Module):
+    """resample.py:36-49 (buffer ``lowpass.filter``)."""
+
+    def __init__(self, ratio=2, kernel_size=12):
+        super().__init__()
+        self.ratio = ratio
+        self.lowpass = _Filter(ratio, kernel_size)
+
+
+class Activation1d(nn.Module):
+    """alias_free_torch/act.py:9-29 and alias_free_activation/cuda/activation1d.py:34-76.
+
+    ``forward`` is the B200 replacement of the reference's fused native op
+    (``anti_alias_activation_cuda.forward``) with the torch path's exact edge semantics."""
+
+    def __init__(self, activation, up_ratio=2, down_ratio=2, up_kernel_size=12, down_kernel_size=12):
+        super().__init__()
+        if (up_ratio, down_ratio, up_kernel_size, down_kernel_size) != (2, 2, 12, 12):
+            raise NotImplementedError("only the 2x / 12-tap anti-aliased activation is implemented")
+        self.up_ratio, self.down_ratio = up_ratio, down_ratio
+        self.act = activation
+        self.upsample = UpSample1d(up_ratio, up_kernel_size)
+        self.downsample = DownSample1d(down_ratio, down_kernel_size)
+
+    def forward(self, x):
+        from .ops import activation1d
+
+        return activation1d(x, self.upsample.filter, self.downsample.lowpass.filter,
+                            self.act.alpha, self.act.beta, self.act.alpha_logscale)
+
+
+class AMPBlock1(nn.Module):
+    """models.py:20-80 — parameter layout of one anti-aliased multi-periodicity block."""
+
+    def __init__(self, h, channels, kernel_size=3, dilation=(1, 3, 5), activation=None):
+        super().__init__()
+        self.h = h
+        self.kernel_size = kernel_size
+        self.dilation = tuple(dilation)
+        self.convs1 = nn.ModuleList(
+            weight_norm(Conv1d(channels, channels, kernel_size, 1, dilation=d,
+                               padding=get_padding(kernel_size, d))) for d in dilation)
+        self.convs1.apply(init_weights)
+        self.convs2 = nn.ModuleList(
+            weight_norm(Conv1d(channels, channels, kernel_size, 1, dilation=1,
+                               padding=get_padding(kernel_size, 1))) for _ in dilation)
+        self.convs2.apply(init_weights)
+        self.num_layers = len(self.convs1) + len(self.convs2)
+        if activation != "snakebeta":
+            raise NotImplementedError("only activation='snakebeta' (config.yaml:106) is implemented")
+        self.activations = nn.ModuleList(
+            Activation1d(activation=SnakeBeta(channels, alpha_logscale=h.snake_logscale))
+            for _ in range(self.num_layers))
+
+    def forward(self, x):
+        """Per-op path (tests): six fused activation+conv launches (models.py:65-74)."""
+        from .ops import amp_layer
+
+        acts1, acts2 = self.activations[::2], self.activations[1::2]
+        for c1, c2, a1, a2 in zip(self.convs1, self.convs2, acts1, acts2):
+            xt = amp_layer(x, c1, a1)
+            x = amp_layer(xt, c2, a2, resid=x)
+        return x
+
+    def remove_weight_norm(self):
+        for l in list(self.convs1) + list(self.convs2):
+            remove_weight_norm(l)
+
+
+def folded_weight(m: nn.Module) -> torch.Tensor:
+    """w = g*v/||v|| in fp32 when weight-norm is still attached (its cached ``weight`` is only
+    refreshed by the forward pre-hook, which this module never triggers), else ``weight``."""
+    if hasattr(m, "weight_g"):
+        return torch._weight_norm(m.weight_v.detach().float(), m.weight_g.detach().float(), 0)
+    return m.weight.detach().float()
+
+
+class BigVGAN(nn.Module):
+    """B200-native BigVGAN generator with the reference's constructor / forward / checkpoint
+    layout (models.py:130-262)."""
+
+    def __init__(self, h, use_cuda_kernel=False):
+        super().__init__()
+        self.h = h
+        # models.py:142 writes the flag into the config; here the CUDA path is the ONLY path,
+        # so the flag is recorded but changes nothing.
+        self.h["use_cuda_kernel"] = use_cuda_kernel
+        self.num_kernels = len(h.resblock_kernel_sizes)
+        self.num_upsamples = len(h.upsample_rates)
+        self.feat_upsample = h.feat_upsample
+        self.cond_in_each_up_layer = h.cond_d_vector_in_each_upsampling_layer
+        if h.resblock != "1":
+            raise NotImplementedError("only resblock '1' (AMPBlock1, config.yaml:94) is implemented")
+
+        c0 = h.upsample_initial_channel
+        self.conv_pre = weight_norm(Conv1d(h.gpt_dim, c0, 7, 1, padding=3))
+        self.ups = nn.ModuleList()
+        for i, (u, k) in enumerate(zip(h.upsample_rates, h.upsample_kernel_sizes)):
+            self.ups.append(nn.ModuleList([
+                weight_norm(ConvTranspose1d(c0 // (2 ** i), c0 // (2 ** (i + 1)), k, u,
+                                            padding=(k - u) // 2))]))
+        self.resblocks = nn.ModuleList()
+        ch = c0
+        for i in range(len(self.ups)):
+            ch = c0 // (2 ** (i + 1))
+            for k, d in zip(h.resblock_kernel_sizes, h.resblock_dilation_sizes):
+                self.resblocks.append(AMPBlock1(h, ch, k, d, activation=h.activation))
+        if h.activation != "snakebeta":
+            raise NotImplementedError("only activation='snakebeta' is implemented")
+        self.activation_post = Activation1d(activation=SnakeBeta(ch, alpha_logscale=h.snake_logscale))
+        self.conv_post = weight_norm(Conv1d(ch, 1, 7, 1, padding=3))
+        for i in range(len(self.ups)):
+            self.ups[i].apply(init_weights)
+        self.conv_post.apply(init_weights)
+
+        self.speaker_encoder = ECAPA_TDNN(h.num_mels, lin_neurons=h.speaker_embedding_dim)
+        self.cond_layer = nn.Conv1d(h.speaker_embedding_dim, c0, 1)
+        if self.cond_in_each_up_layer:
+            self.conds = nn.ModuleList(
+                nn.Conv1d(h.speaker_embedding_dim, c0 // (2 ** (i + 1)), 1)
+                for i in range(len(self.ups)))
+
+        # --- native state (not part of the state dict) ---
+        self._plan: Optional[C.c_void_p] = None
+        self._plan_device: Optional[torch.device] = None
+        self._weights_dirty = True
+        self.precision: Optional[str] = None       # None = follow parameter dtype
+        self.cache_speaker_embedding = False
+        self._spk_cache = None
+        self.register_load_state_dict_post_hook(lambda mod, _keys: mod._invalidate())
+
+    # ---------------------------------------------------------------- nn.Module plumbing
+    def _invalidate(self):
+        self._weights_dirty = True
+        self._spk_cache = None
+
+    def _apply(self, fn, *a, **k):       # .to() / .half() / .cuda() change the weights we packed
+        self._invalidate()
+        return super()._apply(fn, *a, **k)
+
+    def remove_weight_norm(self):
+        """models.py:254-262"""
+        for l in self.ups:
+            for l_i in l:
+                remove_weight_norm(l_i)
+        for l in self.resblocks:
+            l.remove_weight_norm()
+        remove_weight_norm(self.conv_pre)
+        remove_weight_norm(self.conv_post)
+        self._invalidate()
+
+    def __del__(self):
+        try:
+            if self._plan is not None:
+                _lib.load().bvg_plan_destroy(self._plan)
+                self._plan = None
+        except Exception:
+            pass
+
+    # ---------------------------------------------------------------- native plan
+    def _config_struct(self) -> "_lib.BvgConfig":
+        h = self.h
+        cfg = _lib.BvgConfig()
+        cfg.gpt_dim = int(h.gpt_dim)
+        cfg.upsample_initial_channel = int(h.upsample_initial_channel)
+        cfg.num_upsamples = len(h.upsample_rates)
+        for i, (u, k) in enumerate(zip(h.upsample_rates, h.upsample_kernel_sizes)):
+            cfg.upsample_rates[i] = int(u)
+            cfg.upsample_kernel_sizes[i] = int(k)
+        cfg.num_kernels = len(h.resblock_kernel_sizes)
+        for j, (k, ds) in enumerate(zip(h.resblock_kernel_sizes, h.resblock_dilation_sizes)):
+            cfg.resblock_kernel_sizes[j] = int(k)
+            for m, d in enumerate(ds):
+                cfg.resblock_dilation_sizes[j][m] = int(d)
+        cfg.speaker_embedding_dim = int(h.speaker_embedding_dim)
+        cfg.cond_in_each_up_layer = int(bool(self.cond_in_each_up_layer))
+        cfg.snake_logscale = int(bool(h.snake_logscale))
+        return cfg
+
+    def generator_tensors(self) -> Dict[str, torch.Tensor]:
+        """Folded fp32 generator tensors in the reference's post-remove_weight_norm naming."""
+        out: Dict[str, torch.Tensor] = {}
+        for name, m in self.named_modules():
+            if name.startswith("speaker_encoder"):
+                continue
+            if isinstance(m, (Conv1d, ConvTranspose1d)):
+                out[name + ".weight"] = folded_weight(m).contiguous()
+                out[name + ".bias"] = m.bias.detach().float().contiguous()
+            elif isinstance(m, SnakeBeta):
+                out[name + ".alpha"] = m.alpha.detach().float().contiguous()
+                out[name + ".beta"] = m.beta.detach().float().contiguous()
+            elif isinstance(m, _Filter):
+                out[name + ".filter"] = m.filter.detach().float().contiguous()
+        return out
+
+    def _ensure_plan(self, device: torch.device):
+        lib = _lib.load()
+        if device.type != "cuda":
+            raise RuntimeError("BigVGAN (B200-native) runs on CUDA only; there is no CPU fallback. "
+                               f"Got input on {device}.")
+        if self._plan is not None and self._plan_device != device:
+            lib.bvg_plan_destroy(self._plan)
+            self._plan = None
+        if self._plan is None:
+            p = C.c_void_p()
+            cfg = self._config_struct()
+            _lib.check(lib.bvg_plan_create(C.byref(cfg), device.index or 0, C.byref(p)),
+                       "bvg_plan_create")
+            self._plan, self._plan_device = p, device
+            self._weights_dirty = True
+        if self._weights_dirty:
+            tensors = {k: v.to(device) for k, v in self.generator_tensors().items()}
+            descs = (_lib.BvgTensorDesc * len(tensors))()
+            for d, (k, v) in zip(descs, tensors.items()):
+                d.name = k.encode()
+                d.data = v.data_ptr()
+                d.dtype = _lib.BVG_F32
+                d.ndim = v.dim()
+                for i, s in enumerate(v.shape):
+                    d.shape[i] = s
+            with torch.cuda.device(device):
+                _lib.check(lib.bvg_plan_load_weights(self._plan, descs, len(tensors),
+                                                     _lib.stream_ptr(device)),
+                           "bvg_plan_load_weights")
+            self._weights_dirty = False
+        return self._plan
+
+    def _precision_code(self) -> int:
+        if self.precision is not None:
+            return {"fp32": _lib.PREC_F32, "bf16": _lib.PREC_BF16}[self.precision]
+        dt = self.conv_post.bias.dtype
+        return _lib.PREC_F32 if dt == torch.float32 else _lib.PREC_BF16
+
+    # ---------------------------------------------------------------- the hot path
+    def speaker_embedding(self, mel_ref, lens=None) -> torch.Tensor:
+        """models.py:204 — [B,Tm,num_mels] -> [B,1,D] (PyTorch ECAPA), optionally cached."""
+        key = None
+        if self.cache_speaker_embedding and lens is None:
+            st = mel_ref.untyped_storage()
+            key = (st.data_ptr(), mel_ref.storage_offset(), tuple(mel_ref.shape),
+                   tuple(mel_ref.stride()), mel_ref.dtype, mel_ref._version)
+            if self._spk_cache is not None and self._spk_cache[0] == key:
+                return self._spk_cache[2]
+        pdt = self.conv_post.bias.dtype
+        if pdt != torch.float32 and mel_ref.is_cuda and not torch.is_autocast_enabled():
+            with torch.autocast("cuda", dtype=pdt):
+                emb = self.speaker_encoder(mel_ref, lens)
+        else:
+            emb = self.speaker_encoder(mel_ref, lens)
+        if key is not None:
+            self._spk_cache = (key, mel_ref.untyped_storage(), emb)   # storage kept alive
+        return emb
+
+    def decode(self, x: torch.Tensor, speaker_embedding: torch.Tensor,
+               lengths: Optional[Sequence[int]] = None, out_dtype=None) -> torch.Tensor:
+        """models.py:212-252 on the GPU.  x [B,T,gpt_dim]; speaker_embedding [B|1,1,D] or [B|1,D];
+        lengths: valid latent frames per utterance (ragged batch)."""
+        lib = _lib.load()
+        if x.dim() != 3 or x.shape[-1] != self.h.gpt_dim:
+            raise ValueError(f"latent must be [B,T,{self.h.gpt_dim}], got {tuple(x.shape)}")
+        plan = self._ensure_plan(x.device)
+        B, T, _ = x.shape
+        x = x.contiguous()
+        emb = speaker_embedding.reshape(speaker_embedding.shape[0], -1).float()
+        if emb.shape[0] == 1 and B > 1:
+            emb = emb.expand(B, -1)
+        if emb.shape[0] != B:
+            raise ValueError(f"speaker embedding batch {emb.shape[0]} != latent batch {B}")
+        emb = emb.contiguous()
+        up = 1
+        for u in self.h.upsample_rates:
+            up *= int(u)
+        if out_dtype is None:
+            out_dtype = x.dtype if x.dtype in (torch.float32, torch.bfloat16, torch.float16) \
+                else torch.float32
+        wav = torch.empty(B, 1, T * up, device=x.device, dtype=out_dtype)
+        lens_arr = None
+        if lengths is not None:
+            if len(lengths) != B:
+                raise ValueError("lengths must have one entry per utterance")
+            lens_arr = (C.c_int32 * B)(*[int(v) for v in lengths])
+        with torch.cuda.device(x.device):
+            _lib.check(lib.bvg_decode(plan, x.data_ptr(), _lib.torch_dtype_code(x.dtype), lens_arr,
+                                      B, T, emb.data_ptr(), wav.data_ptr(),
+                                      _lib.torch_dtype_code(out_dtype), self._precision_code(),
+                                      _lib.stream_ptr(x.device)), "bvg_decode")
+        return wav
+
+    def forward(self, x, mel_ref, lens=None):
+        """models.py:203-252.  Returns ``(wav [B,1,T*prod(upsample_rates)], None)``."""
+        speaker_embedding = self.speaker_embedding(mel_ref, lens)
+        n_batch = x.size(0)
+        if n_batch * 2 == speaker_embedding.size(0):
+            # models.py:207-209 reaches self.logit_scale, which the reference comments out (:201)
+            raise AttributeError("'BigVGAN' object has no attribute 'logit_scale'")
+        if self.feat_upsample:
+            raise NotImplementedError("feat_upsample=true (models.py:216-220) is not on the "
+                                      "configured path (config.yaml:100)")
+        return self.decode(x, speaker_embedding), None
+
+    @torch.no_grad()
+    def decode_ragged(self, latents: Sequence[torch.Tensor], mel_ref, lens=None):
+        """Batch of variable-length utterances in ONE launch sequence (replaces infer_fast's
+        time-concat, infer.py:726-735): returns a list of [1, T_b*up] waveforms, each equal to
+        an independent ``forward`` on that utterance."""
+        lengths = [int(l.shape[-2]) for l in latents]
+        Tmax = max(lengths)
+        dev, dt = latents[0].device, latents[0].dtype
+        x = torch.zeros(len(latents), Tmax, self.h.gpt_dim, device=dev, dtype=dt)
+        for b, l in enumerate(latents):
+            x[b, : lengths[b]] = l.reshape(lengths[b], -1)
+        emb = self.speaker_embedding(mel_ref, lens)
+        wav = self.decode(x, emb, lengths=lengths)
+        up = wav.shape[-1] // Tmax
+        return [wav[b, :, : lengths[b] * up] for b in range(len(latents))]
