@@ -114,10 +114,11 @@ int bvg_decode(bvg_plan* plan, const void* latent, int latent_dtype, const int32
                int B, int Tmax, const float* spk_emb, void* wav_out, int wav_dtype,
                int precision, void* stream);
 
-/* Same, with HOST buffers (pinned for async copies): H2D of latent + spk_emb, decode, D2H of
- * wav, then synchronises `stream`.  This is the end-to-end call bench.py times as `e2e`. */
+/* Same, with HOST buffers for the bulk data (pinned for async copies): H2D of the latent,
+ * decode, D2H of wav, then synchronises `stream`.  `spk_emb` stays a DEVICE pointer (the ECAPA
+ * encoder runs on the device).  This is the end-to-end call bench.py times as `e2e`. */
 int bvg_decode_host(bvg_plan* plan, const void* latent_host, int latent_dtype,
-                    const int32_t* lengths, int B, int Tmax, const float* spk_emb_host,
+                    const int32_t* lengths, int B, int Tmax, const float* spk_emb,
                     void* wav_out_host, int wav_dtype, int precision, void* stream);
 
 /* Time-split decode of one long utterance shard (BASELINE config 5): decodes latent frames
@@ -139,6 +140,21 @@ int bvg_receptive_field_frames(const bvg_plan* plan);
  * gpu_launches). */
 int64_t bvg_plan_workspace_bytes(const bvg_plan* plan);
 int bvg_plan_last_launches(const bvg_plan* plan);
+
+/* Optional per-launch device timing (CUDA events on the caller's stream around every kernel of
+ * a decode), accumulated per class until read.  Classes: 0 = fused AMP layers of the
+ * tensor-bound stages (C >= 192), 1 = fused AMP layers of the small-channel stages, 2 =
+ * conv_pre / ConvTranspose1d / cond, 3 = activation_post + conv_post + tanh. */
+#define BVG_PROFILE_CLASSES 4
+typedef struct bvg_profile {
+  double ms[BVG_PROFILE_CLASSES];     /* summed device time */
+  double flops[BVG_PROFILE_CLASSES];  /* algorithmic FLOPs (2*Cin*Cout*k per output sample, valid samples) */
+  double bytes[BVG_PROFILE_CLASSES];  /* algorithmic HBM bytes (in + out [+ resid] + weights once) */
+  int32_t launches[BVG_PROFILE_CLASSES];
+} bvg_profile;
+int bvg_plan_set_profiling(bvg_plan* plan, int enable);
+/* Synchronises the events recorded so far, adds them up, clears the accumulators. */
+int bvg_plan_read_profile(bvg_plan* plan, bvg_profile* out);
 
 /* ---- per-op entry points (tests, and the reference's own native-op boundary) ---------- */
 

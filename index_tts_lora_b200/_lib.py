@@ -42,6 +42,14 @@ class BvgTensorDesc(C.Structure):
     ]
 
 
+PROFILE_CLASSES = 4
+
+
+class BvgProfile(C.Structure):
+    _fields_ = [("ms", C.c_double * PROFILE_CLASSES), ("flops", C.c_double * PROFILE_CLASSES),
+                ("bytes", C.c_double * PROFILE_CLASSES), ("launches", C.c_int32 * PROFILE_CLASSES)]
+
+
 # every symbol include/bvg.h declares: name -> (restype, argtypes)
 _P, _I, _L = C.c_void_p, C.c_int, C.c_int64
 SYMBOLS = {
@@ -56,6 +64,8 @@ SYMBOLS = {
     "bvg_receptive_field_frames": (_I, [_P]),
     "bvg_plan_workspace_bytes": (_L, [_P]),
     "bvg_plan_last_launches": (_I, [_P]),
+    "bvg_plan_set_profiling": (_I, [_P, _I]),
+    "bvg_plan_read_profile": (_I, [_P, C.POINTER(BvgProfile)]),
     "bvg_activation1d": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P]),
     "bvg_amp_layer": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P]),
     "bvg_conv_transpose1d": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _P]),

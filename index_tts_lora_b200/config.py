@@ -50,7 +50,7 @@ def default_config() -> AttrDict:
     return AttrDict(copy.deepcopy(DEFAULT_BIGVGAN_CONFIG))
 
 
-def tiny_config(c0: int = 64, gpt_dim: int = 32, num_mels: int = 20, spk: int = 16) -> AttrDict:
+def tiny_config(c0: int = 512, gpt_dim: int = 32, num_mels: int = 20, spk: int = 16) -> AttrDict:
     """A structurally identical but small generator for fast CPU-side tests."""
     h = default_config()
     h.update(upsample_initial_channel=c0, gpt_dim=gpt_dim, num_mels=num_mels,

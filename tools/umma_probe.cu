@@ -1,0 +1,282 @@
+// umma_probe.cu — hardware probe for the design decisions of the fused AMP kernel:
+//  1. tcgen05.mma kind::f16 with SWIZZLE_NONE K-major operands laid out [K/8][rows][8] bf16
+//     (SBO = 128 B => rows linear at 16 B), and a conv-tap shift expressed as a start-address
+//     offset of 16*shift bytes in the A descriptor.
+//  2. sustained cycles per MMA for that layout (M=128, N in {32,96,192,256}).
+//  3. FP32 pipe: FFMA vs fma.rn.f32x2 throughput (decides the FIR/snake stage's math form).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o umma_probe umma_probe.cu
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(2); } } while (0)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;  // descriptor version (Blackwell)
+  return d;         // base_offset 0, lbo_mode 0, layout SWIZZLE_NONE (0)
+}
+
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+  uint32_t d = 0;
+  d |= 1u << 4;                    // D = F32
+  d |= 1u << 7;                    // A = BF16
+  d |= 1u << 10;                   // B = BF16
+  d |= (uint32_t)(N >> 3) << 17;   // N
+  d |= (uint32_t)(M >> 4) << 24;   // M
+  return d;                        // A,B K-major, dense, no negate
+}
+
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\tWAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// ---------------------------------------------------------------- test 1: correctness with shift
+// A smem: [KC/8][ROWS][8] bf16; B smem: [KC/8][N][8] bf16.  D[m][n] = sum_k A[m+shift][k]*B[n][k]
+template <int N, int KC, int ROWS>
+__global__ void __launch_bounds__(128) k_probe(const __nv_bfloat16* A, const __nv_bfloat16* B, float* D, int shift,
+                                               int swap_lbo_sbo) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __nv_bfloat16* sA = (__nv_bfloat16*)smem;                       // KC/8 * ROWS * 8
+  __nv_bfloat16* sB = sA + (KC / 8) * ROWS * 8;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid / 32;
+  // A global is [ROWS][KC] row-major, B global is [N][KC]
+  for (int i = tid; i < ROWS * KC; i += 128) {
+    int r = i / KC, k = i % KC;
+    sA[((k / 8) * ROWS + r) * 8 + (k % 8)] = A[i];
+  }
+  for (int i = tid; i < N * KC; i += 128) {
+    int n = i / KC, k = i % KC;
+    sB[((k / 8) * N + n) * 8 + (k % 8)] = B[i];
+  }
+  if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "n"(N <= 32 ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : 256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> async proxy
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tm = tmem_base;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc(128, N);
+    uint32_t lboA = ROWS * 16, sboA = 128, lboB = N * 16, sboB = 128;
+    if (swap_lbo_sbo) { uint32_t t = lboA; lboA = sboA; sboA = t; t = lboB; lboB = sboB; sboB = t; }
+    for (int ks = 0; ks < KC / 16; ++ks) {
+      uint64_t ad = make_desc(smem_u32(sA) + shift * 16 + ks * 2 * ROWS * 16, lboA, sboA);
+      uint64_t bd = make_desc(smem_u32(sB) + ks * 2 * N * 16, lboB, sboB);
+      mma_bf16(tm, ad, bd, idesc, ks > 0);
+    }
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  // each warp reads its 32 lanes, N columns, 8 at a time
+  const int row = warp * 32 + (tid & 31);
+  for (int c0 = 0; c0 < N; c0 += 8) {
+    uint32_t v[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(tm + ((uint32_t)(warp * 32) << 16) + c0));
+    asm volatile("tcgen05.wait::ld.sync.aligned;");
+    for (int j = 0; j < 8; ++j) D[row * N + c0 + j] = __uint_as_float(v[j]);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "n"(N <= 32 ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : 256));
+}
+
+template <int N, int KC, int ROWS>
+static bool run_probe(int shift, int swap) {
+  std::vector<__nv_bfloat16> hA(ROWS * KC), hB(N * KC);
+  std::vector<float> fA(ROWS * KC), fB(N * KC);
+  srand(1234 + shift);
+  for (int i = 0; i < ROWS * KC; ++i) { float v = (rand() % 2001 - 1000) / 1000.f; hA[i] = __float2bfloat16(v); fA[i] = __bfloat162float(hA[i]); }
+  for (int i = 0; i < N * KC; ++i) { float v = (rand() % 2001 - 1000) / 1000.f; hB[i] = __float2bfloat16(v); fB[i] = __bfloat162float(hB[i]); }
+  __nv_bfloat16 *dA, *dB; float* dD;
+  CK(cudaMalloc(&dA, hA.size() * 2)); CK(cudaMalloc(&dB, hB.size() * 2)); CK(cudaMalloc(&dD, 128 * N * 4));
+  CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dD, 0xff, 128 * N * 4));
+  size_t smem = (size_t)(KC / 8) * (ROWS + N) * 16;
+  auto kern = k_probe<N, KC, ROWS>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<1, 128, smem>>>(dA, dB, dD, shift, swap);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("  probe N=%d shift=%d swap=%d: CUDA error %s\n", N, shift, swap, cudaGetErrorString(e)); exit(3); }
+  std::vector<float> hD(128 * N);
+  CK(cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost));
+  double maxerr = 0;
+  for (int m = 0; m < 128; ++m)
+    for (int n = 0; n < N; ++n) {
+      double s = 0;
+      for (int k = 0; k < KC; ++k) s += (double)fA[(m + shift) * KC + k] * fB[n * KC + k];
+      double err = fabs(s - hD[m * N + n]);
+      if (!(err <= 1e30)) err = 1e30;
+      if (err > maxerr) maxerr = err;
+    }
+  printf("  UMMA no-swizzle K-major  N=%-3d KC=%d shift=%-2d swap_lbo_sbo=%d  max|err|=%.3e  %s\n", N, KC, shift, swap, maxerr,
+         maxerr < 1e-3 ? "PASS" : "FAIL");
+  cudaFree(dA); cudaFree(dB); cudaFree(dD);
+  return maxerr < 1e-3;
+}
+
+// ---------------------------------------------------------------- test 2: MMA issue rate
+template <int N>
+__global__ void __launch_bounds__(128) k_mma_rate(long long* cycles, int iters, int nacc) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid / 32;
+  for (int i = tid; i < (int)(48 * 1024 / 4); i += 128) ((uint32_t*)smem)[i] = 0x3c003c00u + i;
+  if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tm = tmem_base;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc(128, N);
+    const int ROWS = 306;
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      // A: [4][ROWS][8] at smem+0 (shifted by it%11 rows), B: [4][N][8] at smem+24KB
+      uint64_t ad = make_desc(smem_u32(smem) + (it % 11) * 16 + (it & 1) * 2 * ROWS * 16, ROWS * 16, 128);
+      uint64_t bd = make_desc(smem_u32(smem) + 24 * 1024 + (it & 1) * 2 * N * 16, N * 16, 128);
+      mma_bf16(tm + (uint32_t)((it % nacc) * N), ad, bd, idesc, 1);
+    }
+    mma_commit(&bar);
+    mbar_wait(&bar, 0);
+    long long t1 = clock64();
+    cycles[blockIdx.x] = t1 - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "n"(512));
+}
+
+template <int N>
+static void run_rate(int nacc, int grid) {
+  long long* d; CK(cudaMalloc(&d, 8 * grid));
+  auto kern = k_mma_rate<N>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
+  const int iters = 4000;
+  kern<<<grid, 128, 48 * 1024>>>(d, iters, nacc);
+  CK(cudaDeviceSynchronize());
+  std::vector<long long> h(grid);
+  CK(cudaMemcpy(h.data(), d, 8 * grid, cudaMemcpyDeviceToHost));
+  double mean = 0; for (auto c : h) mean += c; mean /= grid;
+  printf("  MMA rate M=128 N=%-3d K=16 nacc=%d grid=%-3d: %.1f cyc/MMA  (floor 128*N/256 = %.0f)  -> %.0f MAC/clk/SM\n", N, nacc, grid,
+         mean / iters, 128.0 * N / 256, 128.0 * N * 16 / (mean / iters));
+  cudaFree(d);
+}
+
+// ---------------------------------------------------------------- test 3: FP32 pipe
+__global__ void __launch_bounds__(512) k_ffma(float* out, int iters) {
+  float a[8];
+  for (int i = 0; i < 8; ++i) a[i] = threadIdx.x * 0.001f + i;
+  const float b = 1.0001f, c = 0.5f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = fmaf(a[i], b, c);
+  }
+  float s = 0; for (int i = 0; i < 8; ++i) s += a[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void __launch_bounds__(512) k_ffma2(float* out, int iters) {
+  unsigned long long a[8];
+  for (int i = 0; i < 8; ++i) { float2 v = make_float2(threadIdx.x * 0.001f + i, threadIdx.x * 0.002f + i); a[i] = *(unsigned long long*)&v; }
+  float2 bv = make_float2(1.0001f, 1.0002f), cv = make_float2(0.5f, 0.25f);
+  unsigned long long b = *(unsigned long long*)&bv, c = *(unsigned long long*)&cv;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a[i]) : "l"(b), "l"(c));
+  }
+  float s = 0; for (int i = 0; i < 8; ++i) { float2 v = *(float2*)&a[i]; s += v.x + v.y; }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void __launch_bounds__(512) k_sin(float* out, int iters) {
+  float a[8];
+  for (int i = 0; i < 8; ++i) a[i] = threadIdx.x * 0.001f + i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = __sinf(a[i]);
+  }
+  float s = 0; for (int i = 0; i < 8; ++i) s += a[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <typename F>
+static float time_kernel(F launch) {
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  launch(); CK(cudaDeviceSynchronize());
+  cudaEventRecord(e0); launch(); cudaEventRecord(e1); CK(cudaDeviceSynchronize());
+  float ms; cudaEventElapsedTime(&ms, e0, e1); return ms;
+}
+
+int main() {
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
+  printf("device: %s sm_%d%d, %d SMs, clock %d kHz\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount, prop.clockRate);
+  printf("[1] descriptor semantics (expect swap=0 PASS for every shift)\n");
+  bool ok = true;
+  for (int shift : {0, 1, 3, 5, 8, 25, 50}) ok &= run_probe<64, 64, 192>(shift, 0);
+  if (!ok) { printf("primary LBO/SBO reading failed; not probing the swapped reading (it walks out of smem)\n"); return 1; }
+  ok &= run_probe<256, 32, 192>(7, 0);
+  ok &= run_probe<96, 32, 192>(15, 0);
+  ok &= run_probe<32, 32, 192>(33, 0);
+  ok &= run_probe<192, 32, 192>(2, 0);
+  ok &= run_probe<48, 32, 192>(2, 0);
+  printf("descriptor probe: %s\n", ok ? "ALL PASS" : "SOME FAIL");
+
+  printf("[2] MMA issue rate, SWIZZLE_NONE operands\n");
+  run_rate<256>(2, 1); run_rate<256>(2, 148); run_rate<192>(2, 148); run_rate<96>(4, 148); run_rate<48>(4, 148); run_rate<32>(4, 148);
+  run_rate<256>(1, 148);
+
+  printf("[3] FP32 pipe\n");
+  const int grid = prop.multiProcessorCount * 4, iters = 4096;
+  float* d; CK(cudaMalloc(&d, sizeof(float) * grid * 512));
+  float ms1 = time_kernel([&] { k_ffma<<<grid, 512>>>(d, iters); });
+  float ms2 = time_kernel([&] { k_ffma2<<<grid, 512>>>(d, iters); });
+  float ms3 = time_kernel([&] { k_sin<<<grid, 512>>>(d, iters); });
+  double n1 = (double)grid * 512 * iters * 32;
+  printf("  FFMA      : %.3f ms  %.1f GFMA/s  (%.1f lane-FMA/clk/SM @1.9GHz)\n", ms1, n1 / ms1 / 1e6, n1 / ms1 / 1e6 * 1e9 / 148 / 1.9e9);
+  printf("  FFMA2 x2  : %.3f ms  %.1f GFMA/s  (%.1f lane-FMA/clk/SM @1.9GHz)\n", ms2, 2 * n1 / ms2 / 1e6, 2 * n1 / ms2 / 1e6 * 1e9 / 148 / 1.9e9);
+  printf("  MUFU.SIN  : %.3f ms  %.1f Gsin/s  (%.1f lane-op/clk/SM @1.9GHz)\n", ms3, n1 / ms3 / 1e6, n1 / ms3 / 1e6 * 1e9 / 148 / 1.9e9);
+  return ok ? 0 : 1;
+}
