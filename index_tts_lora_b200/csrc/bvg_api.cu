@@ -50,14 +50,14 @@ static void conv_cost(const Ctx& c, const ConvArgs& a, int K, double* flops, dou
            (double)a.Cin * a.Cout * K * c.elt;
 }
 
-template <int K, bool ACT, int TY, int NC, int NT, bool TM_IN>
+template <int K, bool ACT, int TY, int NC, int NT, int XL>
 static int launch_conv(const ConvArgs& a, int B, const Ctx& c) {
   cudaStream_t st = c.st;
   constexpr int TX = 256 / TY, TT = TX * NT, COB = TY * NC, CK = 8;
   const int hc = a.dil * (K - 1) / 2;
   const int ZW = TT + 2 * hc, SW = 2 * ZW + 12, XW = ZW + 12;
   const size_t smem = sizeof(float) * (size_t)(CK * ZW + CK * K * COB + (ACT ? CK * (SW + XW) : 0));
-  auto kern = k_conv_f32<K, ACT, TY, NC, NT, TM_IN>;
+  auto kern = k_conv_f32<K, ACT, TY, NC, NT, XL>;
   static bool attr_set = false;   // per template instance
   if (!attr_set) {
     BVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -79,25 +79,26 @@ static int launch_conv_k(int K, const ConvArgs& a, int B, const Ctx& c) {
   const bool narrow = a.Cout <= 32;
   switch (K) {
     case 3:
-      return narrow ? launch_conv<3, ACT, 8, 4, 8, false>(a, B, c)
-                    : launch_conv<3, ACT, 16, 4, 8, false>(a, B, c);
+      return narrow ? launch_conv<3, ACT, 8, 4, 8, 0>(a, B, c)
+                    : launch_conv<3, ACT, 16, 4, 8, 0>(a, B, c);
     case 7:
-      return narrow ? launch_conv<7, ACT, 8, 4, 8, false>(a, B, c)
-                    : launch_conv<7, ACT, 16, 4, 8, false>(a, B, c);
+      return narrow ? launch_conv<7, ACT, 8, 4, 8, 0>(a, B, c)
+                    : launch_conv<7, ACT, 16, 4, 8, 0>(a, B, c);
     case 11:
-      return narrow ? launch_conv<11, ACT, 8, 4, 8, false>(a, B, c)
-                    : launch_conv<11, ACT, 16, 4, 8, false>(a, B, c);
+      return narrow ? launch_conv<11, ACT, 8, 4, 8, 0>(a, B, c)
+                    : launch_conv<11, ACT, 16, 4, 8, 0>(a, B, c);
     default:
       return fail(BVG_ERR_UNSUPPORTED, "conv kernel size %d not supported (3, 7, 11)", K);
   }
 }
 
+template <bool BLK>
 static int launch_convtr(const ConvTrArgs& a, int B, const Ctx& c) {
   cudaStream_t st = c.st;
   constexpr int TY = 16, NC = 4, NT = 8, TX = 256 / TY, TT = TX * NT, COB = TY * NC, CK = 8;
   const int QW = TT / a.U + a.KK / a.U + 2;
   const size_t smem = sizeof(float) * (size_t)(CK * QW + CK * a.KK * COB);
-  auto kern = k_convtr_f32<TY, NC, NT>;
+  auto kern = k_convtr_f32<TY, NC, NT, BLK>;
   static bool attr_set = false;
   if (!attr_set) {
     BVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -267,7 +268,7 @@ static int decode_f32(bvg_plan* p, const void* latent, int latent_dtype, const i
     a.out = cur; a.out_dtype = BVG_F32; a.out_tstride = Tmax; a.div = 1.f;
     a.Cin = p->conv_pre.Cin; a.Cout = p->conv_pre.Cout; a.dil = 1;
     a.lengths = d_len; a.rate = 1; a.Tmax = Tmax;
-    if ((rc = launch_conv<7, false, 16, 4, 8, true>(a, B, cx))) return rc;
+    if ((rc = launch_conv<7, false, 16, 4, 8, 1>(a, B, cx))) return rc;
   }
   const int nk = p->cfg.num_kernels;
   for (int i = 0; i < p->n_stages; ++i) {
@@ -288,7 +289,7 @@ static int decode_f32(bvg_plan* p, const void* latent, int latent_dtype, const i
       a.Cin = p->ups[i].Cin; a.Cout = Ci; a.KK = p->ups[i].K; a.U = p->cfg.upsample_rates[i];
       a.lengths = d_len; a.rate_out = Ri; a.Tmax_out = Ti;
       cx.cls = 2;
-      if ((rc = launch_convtr(a, B, cx))) return rc;
+      if ((rc = launch_convtr<false>(a, B, cx))) return rc;
     }
     cx.cls = (Ci >= 192) ? 0 : 1;
     for (int j = 0; j < nk; ++j) {
@@ -340,9 +341,52 @@ static int decode_f32(bvg_plan* p, const void* latent, int latent_dtype, const i
     a.tanh_out = 1; a.zero_tail = 1;
     fill_act(a.act, p->act_post);
     cx.cls = 3;
-    if ((rc = launch_conv<7, true, 1, 1, 2, false>(a, B, cx))) return rc;
+    if ((rc = launch_conv<7, true, 1, 1, 2, 0>(a, B, cx))) return rc;
   }
   return 0;
+}
+
+// ---- SIMT kernels reused by the tcgen05 path (blocked bf16 activations) ----------------------
+int tc_ensure_ws(bvg_plan* p, size_t bytes_per_buf) { return ensure_ws(p, bytes_per_buf); }
+
+// ConvTranspose1d + cond add of stage i (models.py:232-236), blocked bf16 in/out
+int simt_convtr_blk(bvg_plan* p, const void* x_blk, void* out_blk, int i, int B, int Tmax, const int* d_len,
+                    cudaStream_t st) {
+  Ctx cx{p, st, 2, 2.0};
+  ConvTrArgs a{};
+  a.x = x_blk; a.x_tstride = Tmax * p->rate[i];
+  a.wp = p->ups[i].wp; a.bias = p->ups[i].bias;
+  a.bias_b = p->cfg.cond_in_each_up_layer ? p->condb + p->cond_off[i + 1] : nullptr;
+  a.bias_b_stride = p->cond_total;
+  a.out = out_blk; a.out_tstride = Tmax * p->rate[i + 1];
+  a.Cin = p->ups[i].Cin; a.Cout = p->C[i + 1]; a.KK = p->ups[i].K; a.U = p->cfg.upsample_rates[i];
+  a.lengths = d_len; a.rate_out = p->rate[i + 1]; a.Tmax_out = Tmax * p->rate[i + 1];
+  return launch_convtr<true>(a, B, cx);
+}
+
+// activation_post + conv_post + tanh (models.py:248-250) from the blocked bf16 stage output
+int simt_post_blk(bvg_plan* p, const void* x_blk, void* wav, int wav_dtype, int B, int Tmax, const int* d_len,
+                  cudaStream_t st) {
+  const int S = p->n_stages;
+  Ctx cx{p, st, 3, 2.0};
+  ConvArgs a{};
+  a.x = x_blk; a.x_tstride = Tmax * p->rate[S];
+  a.wp = p->conv_post.wp; a.bias = p->conv_post.bias;
+  a.out = wav; a.out_dtype = wav_dtype; a.out_tstride = Tmax * p->rate[S]; a.div = 1.f;
+  a.Cin = p->C[S]; a.Cout = 1; a.dil = 1;
+  a.lengths = d_len; a.rate = p->rate[S]; a.Tmax = Tmax * p->rate[S];
+  a.tanh_out = 1; a.zero_tail = 1;
+  fill_act(a.act, p->act_post);
+  return launch_conv<7, true, 1, 1, 2, 2>(a, B, cx);
+}
+
+void tc_pack_conv_w(const float* w, float* wp, int Cout, int Cin, int K, cudaStream_t st) {
+  const size_t n = (size_t)Cout * Cin * K;
+  k_pack_conv_w<<<(int)std::min<size_t>((n + 255) / 256, 4096), 256, 0, st>>>(w, wp, Cout, Cin, K);
+}
+void tc_snake_params(const float* alpha, const float* beta, float* a, float* invb, int C, int logscale,
+                     cudaStream_t st) {
+  k_snake_params<<<ceil_div(C, 128), 128, 0, st>>>(alpha, beta, a, invb, C, logscale);
 }
 
 static int check_device(int device, int* sm_count) {
@@ -721,7 +765,7 @@ int bvg_conv_transpose1d(const float* x, float* y, int B, int C_in, int C_out, i
   a.Cin = C_in; a.Cout = C_out; a.KK = k; a.U = u;
   a.lengths = nullptr; a.rate_out = u; a.Tmax_out = T * u;
   Ctx cx{nullptr, st, 2, 4.0};
-  rc = launch_convtr(a, B, cx);
+  rc = launch_convtr<false>(a, B, cx);
   cudaFreeAsync(wp, st);
   return rc;
 }

@@ -1,14 +1,417 @@
-// decode_tc.cu — bf16 tcgen05/TMEM path (placeholder until the kernel lands).
+// decode_tc.cu — host side of the bf16 tcgen05/TMEM path: weight tiling, TMA tensor maps,
+// launch selection and the decode orchestration (models.py:212-252) on the blocked bf16 layout.
+#include <cuda.h>
+
+#include <map>
+#include <tuple>
+#include <vector>
+
+#include "amp_tc.cuh"
 #include "tc_api.h"
+
 namespace bvg {
-int tc_plan_pack(bvg_plan*, cudaStream_t) { return 0; }
-void tc_plan_free(bvg_plan*) {}
-int64_t tc_plan_workspace_bytes(const bvg_plan*) { return 0; }
-int tc_decode(bvg_plan*, const void*, int, const int32_t*, const int*, int, int, void*, int, cudaStream_t) {
-  return fail(BVG_ERR_UNSUPPORTED, "bf16 tcgen05 path not built yet");
+using namespace tc;
+
+// ------------------------------------------------------------------------------ small kernels
+// folded fp32 tap-major weights [Cin][K][Cout] -> bf16 UMMA tiles [ntile][chunk][tap][4][n_tile][8]
+__global__ void k_pack_wt(const float* __restrict__ wp, __nv_bfloat16* __restrict__ wt, int Cin, int Cout,
+                          int K, int n_tile, int NCH, int NT) {
+  const size_t total = (size_t)NT * NCH * K * 32 * n_tile;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int e = idx % 8;
+    size_t r = idx / 8;
+    const int n = r % n_tile; r /= n_tile;
+    const int kg = r % 4; r /= 4;
+    const int j = r % K; r /= K;
+    const int c = r % NCH;
+    const int nt = r / NCH;
+    const int co = nt * n_tile + n, ci = c * 32 + kg * 8 + e;
+    float v = 0.f;
+    if (co < Cout && ci < Cin) v = wp[((size_t)ci * K + j) * Cout + co];
+    wt[idx] = __float2bfloat16_rn(v);
+  }
 }
-int tc_amp_layer(const float*, float*, const float*, int, int, int, int, const float*, const float*, int,
-                 int, int, const float*, const float*, const float*, const float*, int, cudaStream_t) {
-  return fail(BVG_ERR_UNSUPPORTED, "bf16 tcgen05 path not built yet");
+
+// a2 = 2*exp(alpha), nhb = -0.5/(exp(beta)+1e-9), zero-padded to a multiple of 32 channels
+__global__ void k_tc_params(const float* a, const float* invb, float* a2, float* nhb, int C, int Cpad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cpad) return;
+  a2[i] = i < C ? 2.0f * a[i] : 0.f;
+  nhb[i] = i < C ? -0.5f * invb[i] : 0.f;
 }
+
+// latent [B][Tmax][C] (f32/bf16/f16, time-major as the GPT emits it, gpt/model.py:459-474) ->
+// blocked bf16 [B][C/8][Tmax][8], zero beyond each utterance's length.
+__global__ void k_latent_blk(const void* __restrict__ lat, int dtype, __nv_bfloat16* __restrict__ out, int C,
+                             int Tmax, const int* __restrict__ lengths) {
+  const int b = blockIdx.z, cg = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= Tmax) return;
+  const int T = lengths ? lengths[b] : Tmax;
+  __nv_bfloat16 v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+    v[e] = __float2bfloat16_rn(t < T ? ld_dyn(lat, ((size_t)b * Tmax + t) * C + cg * 8 + e, dtype) : 0.f);
+  *reinterpret_cast<uint4*>(out + (((size_t)b * (C >> 3) + cg) * Tmax + t) * 8) = *reinterpret_cast<uint4*>(v);
+}
+
+// per-op helpers: channel-major fp32 [B][C][T] <-> blocked bf16
+__global__ void k_cm_to_blk(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int C, int T) {
+  const int b = blockIdx.z, cg = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  __nv_bfloat16 v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = __float2bfloat16_rn(x[((size_t)b * C + cg * 8 + e) * T + t]);
+  *reinterpret_cast<uint4*>(out + (((size_t)b * (C >> 3) + cg) * T + t) * 8) = *reinterpret_cast<uint4*>(v);
+}
+__global__ void k_blk_to_cm(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int C, int T) {
+  const int b = blockIdx.z, cg = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  uint4 raw = *reinterpret_cast<const uint4*>(x + (((size_t)b * (C >> 3) + cg) * T + t) * 8);
+  const __nv_bfloat16* v = reinterpret_cast<const __nv_bfloat16*>(&raw);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) out[((size_t)b * C + cg * 8 + e) * T + t] = __bfloat162float(v[e]);
+}
+
+// ------------------------------------------------------------------------------ plan state
+struct TcLayer {
+  __nv_bfloat16* wt = nullptr;
+  float* a2 = nullptr;
+  float* nhb = nullptr;
+  int n_tile = 0, n_tiles = 0, tps = 1, tmem_cols = 32, nch = 0;
+};
+
+struct TcPlan {
+  TcLayer pre;
+  TcLayer rb1[kMaxBlocks][BVG_MAX_DIL], rb2[kMaxBlocks][BVG_MAX_DIL];
+  void* lat_blk = nullptr;
+  size_t lat_bytes = 0;
+  std::map<std::tuple<const void*, int, int, int>, CUtensorMap> maps;
+  std::vector<void*> owned;
+};
+
+static void pick_tile(int Cout, int* n_tile, int* n_tiles) {
+  if (Cout <= 256) {
+    *n_tile = std::max(16, (Cout + 15) / 16 * 16);
+    *n_tiles = 1;
+    return;
+  }
+  for (int nt = (Cout + 255) / 256;; ++nt) {
+    if (Cout % nt == 0 && (Cout / nt) % 16 == 0) {
+      *n_tile = Cout / nt;
+      *n_tiles = nt;
+      return;
+    }
+  }
+}
+
+static int pow2_cols(int need) {
+  int c = 32;
+  while (c < need) c <<= 1;
+  return c;
+}
+
+static int build_layer(std::vector<void*>& owned, TcLayer& L, const ConvW& cw, const ActW* aw, cudaStream_t st) {
+  pick_tile(cw.Cout, &L.n_tile, &L.n_tiles);
+  L.nch = (cw.Cin + KC - 1) / KC;
+  L.tps = std::max(1, std::min(cw.K, W_STAGE_BYTES / (L.n_tile * 64)));
+  L.tmem_cols = pow2_cols(2 * L.n_tile);
+  const size_t elems = (size_t)L.n_tiles * L.nch * cw.K * 32 * L.n_tile;
+  if (!L.wt) {
+    BVG_CUDA(cudaMalloc((void**)&L.wt, elems * sizeof(__nv_bfloat16)));
+    owned.push_back(L.wt);
+  }
+  k_pack_wt<<<(int)std::min<size_t>((elems + 255) / 256, 8192), 256, 0, st>>>(cw.wp, L.wt, cw.Cin, cw.Cout, cw.K,
+                                                                             L.n_tile, L.nch, L.n_tiles);
+  BVG_CUDA(cudaGetLastError());
+  if (aw) {
+    const int Cpad = L.nch * KC;
+    if (!L.a2) {
+      BVG_CUDA(cudaMalloc((void**)&L.a2, Cpad * sizeof(float)));
+      BVG_CUDA(cudaMalloc((void**)&L.nhb, Cpad * sizeof(float)));
+      owned.push_back(L.a2);
+      owned.push_back(L.nhb);
+    }
+    k_tc_params<<<ceil_div(Cpad, 128), 128, 0, st>>>(aw->a, aw->invb, L.a2, L.nhb, cw.Cin, Cpad);
+    BVG_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+int tc_plan_pack(bvg_plan* p, cudaStream_t st) {
+  if (!p->tc) p->tc = new TcPlan();
+  TcPlan* t = static_cast<TcPlan*>(p->tc);
+  int rc;
+  if ((rc = build_layer(t->owned, t->pre, p->conv_pre, nullptr, st))) return rc;
+  for (int i = 0; i < p->n_stages; ++i)
+    for (int j = 0; j < p->cfg.num_kernels; ++j) {
+      const int n = i * p->cfg.num_kernels + j;
+      for (int m = 0; m < BVG_MAX_DIL; ++m) {
+        const int K = p->rb1[n][m].K, d = p->cfg.resblock_dilation_sizes[j][m];
+        if (d * (K - 1) / 2 > 25 || (K - 1) / 2 > 25)
+          return fail(BVG_ERR_UNSUPPORTED, "tcgen05 path supports conv halos up to 25 samples (k=%d, d=%d)", K, d);
+        if ((rc = build_layer(t->owned, t->rb1[n][m], p->rb1[n][m], &p->rba[n][2 * m], st))) return rc;
+        if ((rc = build_layer(t->owned, t->rb2[n][m], p->rb2[n][m], &p->rba[n][2 * m + 1], st))) return rc;
+      }
+    }
+  return 0;
+}
+
+void tc_plan_free(bvg_plan* p) {
+  if (!p->tc) return;
+  TcPlan* t = static_cast<TcPlan*>(p->tc);
+  for (void* q : t->owned) cudaFree(q);
+  if (t->lat_blk) cudaFree(t->lat_blk);
+  delete t;
+  p->tc = nullptr;
+}
+
+int64_t tc_plan_workspace_bytes(const bvg_plan* p) {
+  return p->tc ? (int64_t) static_cast<TcPlan*>(p->tc)->lat_bytes : 0;
+}
+
+// ------------------------------------------------------------------------------ tensor maps
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<PFN_encodeTiled>(f);
+  }();
+  return fn;
+}
+
+// blocked bf16 activation buffer [B][C/8][Tstride][8] as a 4-D tensor {8, Tstride, C/8, B};
+// box {8, BOXR, 1, 1}; out-of-range rows / channel groups read as zero.
+static int make_map(const void* base, int C, int Tstride, int B, CUtensorMap* out) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return fail(BVG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {8, (cuuint64_t)Tstride, (cuuint64_t)(C / 8), (cuuint64_t)B};
+  cuuint64_t strides[3] = {16, (cuuint64_t)Tstride * 16, (cuuint64_t)(C / 8) * Tstride * 16};
+  cuuint32_t box[4] = {8, (cuuint32_t)BOXR, 1, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(BVG_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) C=%d T=%d B=%d", (int)r, C, Tstride, B);
+  return 0;
+}
+
+static int get_map(TcPlan* t, const void* base, int C, int Tstride, int B, const CUtensorMap** out) {
+  auto key = std::make_tuple(base, C, Tstride, B);
+  auto it = t->maps.find(key);
+  if (it == t->maps.end()) {
+    if (t->maps.size() > 4096) t->maps.clear();
+    CUtensorMap m;
+    int rc = make_map(base, C, Tstride, B, &m);
+    if (rc) return rc;
+    it = t->maps.emplace(key, m).first;
+  }
+  *out = &it->second;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ launch
+struct TcLaunch {
+  const void* x;                // blocked bf16 input
+  const __nv_bfloat16* resid = nullptr;
+  const __nv_bfloat16* acc_in = nullptr;
+  __nv_bfloat16* out = nullptr;
+  float div = 1.f;
+  const float* bias_b = nullptr;
+  int bias_b_stride = 0;
+  int dil = 1;
+  int B = 1, Tstride = 0, rate = 1;
+  const int* d_len = nullptr;
+  int cls = 0;
+};
+
+template <int L, bool ACT>
+static int launch_inst(const CUtensorMap& map, const TcArgs& a, dim3 grid, cudaStream_t st) {
+  auto kern = k_amp_tc<L, ACT>;
+  static bool attr = false;
+  if (!attr) {
+    BVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr = true;
+  }
+  kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(map, a);
+  BVG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, const ConvW& cw, const ActW* aw,
+                     const TcLaunch& q, cudaStream_t st) {
+  TcArgs a{};
+  a.wt = L.wt; a.bias = cw.bias; a.bias_b = q.bias_b; a.bias_b_stride = q.bias_b_stride;
+  a.resid = q.resid; a.acc_in = q.acc_in; a.out = q.out; a.div = q.div;
+  a.Cin = cw.Cin; a.Cout = cw.Cout; a.K = cw.K; a.dil = q.dil;
+  a.n_tile = L.n_tile; a.taps_per_stage = L.tps; a.tmem_cols = L.tmem_cols;
+  a.Tstride = q.Tstride; a.lengths = q.d_len; a.rate = q.rate; a.Tmax = q.Tstride;
+  const int hc = q.dil * (cw.K - 1) / 2;
+  if (aw) {
+    a.a2 = L.a2; a.nhb = L.nhb;
+    for (int i = 0; i < 12; ++i) { a.up2[i] = 2.0f * aw->up[i]; a.dn[i] = aw->dn[i]; }
+  }
+  dim3 grid(ceil_div(q.Tstride, M_TILE), L.n_tiles, q.B);
+  const double samples = (p ? p->cur_sum_frames : 0.0) * q.rate;
+  prof_begin(p, st, q.cls, 2.0 * cw.Cin * cw.Cout * cw.K * samples,
+             samples * 2.0 * (cw.Cin + cw.Cout + (q.resid ? cw.Cout : 0) + (q.acc_in ? cw.Cout : 0)) +
+                 2.0 * cw.Cin * cw.Cout * cw.K);
+  int rc;
+  if (!aw) rc = launch_inst<17, false>(map, a, grid, st);
+  else if (hc <= 8) rc = launch_inst<17, true>(map, a, grid, st);
+  else if (hc <= 24) rc = launch_inst<19, true>(map, a, grid, st);
+  else rc = launch_inst<21, true>(map, a, grid, st);
+  prof_end(p, st);
+  if (p) ++p->last_launches;
+  return rc;
+}
+
+// ------------------------------------------------------------------------------ decode
+int tc_decode(bvg_plan* p, const void* latent, int latent_dtype, const int32_t* h_len, const int* d_len, int B,
+              int Tmax, void* wav_out, int wav_dtype, cudaStream_t st) {
+  (void)h_len;
+  TcPlan* t = static_cast<TcPlan*>(p->tc);
+  if (!t) return fail(BVG_ERR_STATE, "tcgen05 path: weights not packed");
+  int rc;
+  size_t max_elems = (size_t)p->C[0] * Tmax;
+  for (int i = 0; i < p->n_stages; ++i)
+    max_elems = std::max(max_elems, (size_t)p->C[i + 1] * Tmax * p->rate[i + 1]);
+  if ((rc = tc_ensure_ws(p, max_elems * B * sizeof(__nv_bfloat16)))) return rc;
+  const size_t lat_need = (size_t)B * p->cfg.gpt_dim * Tmax * sizeof(__nv_bfloat16);
+  if (lat_need > t->lat_bytes) {
+    BVG_CUDA(cudaDeviceSynchronize());
+    if (t->lat_blk) BVG_CUDA(cudaFree(t->lat_blk));
+    t->lat_blk = nullptr; t->lat_bytes = 0;
+    BVG_CUDA(cudaMalloc(&t->lat_blk, lat_need));
+    t->lat_bytes = lat_need;
+    t->maps.clear();
+  }
+  __nv_bfloat16* bufs[4] = {(__nv_bfloat16*)p->ws[0], (__nv_bfloat16*)p->ws[1], (__nv_bfloat16*)p->ws[2],
+                            (__nv_bfloat16*)p->ws[3]};
+  const CUtensorMap* map;
+
+  // latent -> blocked bf16
+  {
+    dim3 grid(ceil_div(Tmax, 128), p->cfg.gpt_dim / 8, B);
+    prof_begin(p, st, 2, 0.0, (double)B * Tmax * p->cfg.gpt_dim * 6.0);
+    k_latent_blk<<<grid, 128, 0, st>>>(latent, latent_dtype, (__nv_bfloat16*)t->lat_blk, p->cfg.gpt_dim, Tmax, d_len);
+    prof_end(p, st);
+    BVG_CUDA(cudaGetLastError());
+    ++p->last_launches;
+  }
+  // conv_pre + cond_layer add (models.py:226-228): plain conv, TMA tile feeds the MMA directly
+  __nv_bfloat16* cur = bufs[0];
+  {
+    if ((rc = get_map(t, t->lat_blk, p->cfg.gpt_dim, Tmax, B, &map))) return rc;
+    TcLaunch q;
+    q.x = t->lat_blk; q.out = cur; q.bias_b = p->condb + p->cond_off[0]; q.bias_b_stride = p->cond_total;
+    q.dil = 1; q.B = B; q.Tstride = Tmax; q.rate = 1; q.d_len = d_len; q.cls = 2;
+    if ((rc = launch_tc(p, *map, t->pre, p->conv_pre, nullptr, q, st))) return rc;
+  }
+  const int nk = p->cfg.num_kernels;
+  for (int i = 0; i < p->n_stages; ++i) {
+    const int Ci = p->C[i + 1], Ri = p->rate[i + 1], Ti = Tmax * Ri;
+    __nv_bfloat16* free3[3];
+    int nf = 0;
+    for (int qd = 0; qd < 4; ++qd)
+      if (bufs[qd] != cur) free3[nf++] = bufs[qd];
+    __nv_bfloat16 *xin = free3[0], *xr = free3[1], *xt = free3[2], *xs = cur;
+    if ((rc = simt_convtr_blk(p, cur, xin, i, B, Tmax, d_len, st))) return rc;
+    const int cls = (Ci >= 192) ? 0 : 1;
+    for (int j = 0; j < nk; ++j) {
+      const int n = i * nk + j;
+      const __nv_bfloat16* xcur = xin;
+      for (int m = 0; m < BVG_MAX_DIL; ++m) {
+        const int d = p->cfg.resblock_dilation_sizes[j][m];
+        TcLaunch qa;
+        qa.x = xcur; qa.out = xt; qa.dil = d; qa.B = B; qa.Tstride = Ti; qa.rate = Ri; qa.d_len = d_len; qa.cls = cls;
+        if ((rc = get_map(t, xcur, Ci, Ti, B, &map))) return rc;
+        if ((rc = launch_tc(p, *map, t->rb1[n][m], p->rb1[n][m], &p->rba[n][2 * m], qa, st))) return rc;
+
+        const bool last = (m == BVG_MAX_DIL - 1);
+        TcLaunch qb;
+        qb.x = xt; qb.resid = xcur; qb.dil = 1; qb.B = B; qb.Tstride = Ti; qb.rate = Ri; qb.d_len = d_len; qb.cls = cls;
+        if (!last) {
+          qb.out = xr;
+        } else {
+          qb.out = xs;
+          qb.acc_in = (j > 0) ? xs : nullptr;
+          qb.div = (j == nk - 1) ? (float)nk : 1.f;
+        }
+        if ((rc = get_map(t, xt, Ci, Ti, B, &map))) return rc;
+        if ((rc = launch_tc(p, *map, t->rb2[n][m], p->rb2[n][m], &p->rba[n][2 * m + 1], qb, st))) return rc;
+        xcur = xr;
+      }
+    }
+    cur = xs;
+  }
+  return simt_post_blk(p, cur, wav_out, wav_dtype, B, Tmax, d_len, st);
+}
+
+// ------------------------------------------------------------------------------ per-op (tests)
+int tc_amp_layer(const float* x, float* y, const float* resid, int B, int C_in, int C_out, int T, const float* w,
+                 const float* bias, int k, int dilation, int act, const float* up_filter,
+                 const float* down_filter, const float* alpha, const float* beta, int logscale, cudaStream_t st) {
+  BVG_REQUIRE(C_in % 8 == 0 && C_out % 8 == 0, "tcgen05 per-op path: channels must be multiples of 8");
+  const int hc = dilation * (k - 1) / 2;
+  if (hc > 25) return fail(BVG_ERR_UNSUPPORTED, "tcgen05 path supports conv halos up to 25 samples");
+  std::vector<void*> tmp;
+  auto cleanup = [&]() { for (void* q : tmp) cudaFree(q); };
+  auto alloc = [&](void** ptr, size_t bytes) { cudaError_t e = cudaMalloc(ptr, bytes); if (e == cudaSuccess) tmp.push_back(*ptr); return e; };
+  ConvW cw; ActW aw;
+  cw.Cin = C_in; cw.Cout = C_out; cw.K = k;
+  const size_t nw = (size_t)C_out * C_in * k;
+  __nv_bfloat16 *xb, *yb, *rb = nullptr;
+  float *a_dev = nullptr, *invb_dev = nullptr;
+  if (alloc((void**)&cw.wp, nw * 4) || alloc((void**)&xb, (size_t)B * C_in * T * 2) ||
+      alloc((void**)&yb, (size_t)B * C_out * T * 2) || alloc((void**)&a_dev, C_in * 4) || alloc((void**)&invb_dev, C_in * 4) ||
+      (resid && alloc((void**)&rb, (size_t)B * C_out * T * 2))) {
+    cleanup();
+    return fail(BVG_ERR_CUDA, "tc_amp_layer: allocation failed");
+  }
+  cw.bias = const_cast<float*>(bias);
+  tc_pack_conv_w(w, cw.wp, C_out, C_in, k, st);
+  if (act) {
+    tc_snake_params(alpha, beta, a_dev, invb_dev, C_in, logscale, st);
+    aw.a = a_dev; aw.invb = invb_dev; aw.C = C_in;
+    cudaMemcpyAsync(aw.up, up_filter, 48, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(aw.dn, down_filter, 48, cudaMemcpyDeviceToHost, st);
+  }
+  TcLayer L;
+  std::vector<void*> owned;
+  int rc = build_layer(owned, L, cw, act ? &aw : nullptr, st);
+  for (void* q : owned) tmp.push_back(q);
+  if (rc) { cleanup(); return rc; }
+  dim3 g(ceil_div(T, 128), C_in / 8, B);
+  k_cm_to_blk<<<g, 128, 0, st>>>(x, xb, C_in, T);
+  if (resid) {
+    dim3 g2(ceil_div(T, 128), C_out / 8, B);
+    k_cm_to_blk<<<g2, 128, 0, st>>>(resid, rb, C_out, T);
+  }
+  cudaStreamSynchronize(st);   // filter taps on the host
+  CUtensorMap map;
+  if ((rc = make_map(xb, C_in, T, B, &map))) { cleanup(); return rc; }
+  TcLaunch q;
+  q.x = xb; q.resid = rb; q.out = yb; q.dil = dilation; q.B = B; q.Tstride = T; q.rate = 1; q.d_len = nullptr;
+  rc = launch_tc(nullptr, map, L, cw, act ? &aw : nullptr, q, st);
+  if (!rc) {
+    dim3 g3(ceil_div(T, 128), C_out / 8, B);
+    k_blk_to_cm<<<g3, 128, 0, st>>>(yb, y, C_out, T);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = fail(BVG_ERR_CUDA, "tc_amp_layer: %s", cudaGetErrorString(e));
+  }
+  cleanup();
+  return rc;
+}
+
 }  // namespace bvg

@@ -63,8 +63,11 @@ struct ConvArgs {
   ActParams act;
 };
 
-template <int K, bool ACT, int TY, int NC, int NT, bool TM_IN>
+// XL: layout of x — 0 channel-major fp32 [B][Cin][T]; 1 time-major latent [B][Tmax][Cin] (any
+// dtype); 2 blocked bf16 [B][Cin/8][T][8] (the tcgen05 path's layout, used by conv_post there).
+template <int K, bool ACT, int TY, int NC, int NT, int XL>
 __global__ void __launch_bounds__(256) k_conv_f32(const ConvArgs a) {
+  constexpr bool TM_IN = (XL == 1);
   constexpr int TX = 256 / TY;
   constexpr int TT = TX * NT;
   constexpr int COB = TY * NC;
@@ -105,6 +108,7 @@ __global__ void __launch_bounds__(256) k_conv_f32(const ConvArgs a) {
     for (int q = 0; q < NC; ++q) acc[i][q] = 0.f;
 
   const float* xf = reinterpret_cast<const float*>(a.x);
+  const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(a.x);
 
   for (int ci0 = 0; ci0 < a.Cin; ci0 += CK) {
     // ---- stage weights [CK][K][COB] (zero beyond Cout)
@@ -116,10 +120,14 @@ __global__ void __launch_bounds__(256) k_conv_f32(const ConvArgs a) {
     if (ACT) {
       // ---- x window with replicate clamp (resample.py:28)
       for (int idx = tid; idx < CK * XW; idx += 256) {
-        const int c = idx / XW, i = idx % XW;
+        int c, i;
+        if (XL == 2) { c = idx % CK; i = idx / CK; } else { c = idx / XW; i = idx % XW; }
         int t = x_lo + i;
         t = t < 0 ? 0 : (t > T - 1 ? T - 1 : t);
-        xs[idx] = __ldg(xf + ((size_t)b * a.Cin + ci0 + c) * a.x_tstride + t);
+        if (XL == 2)
+          xs[c * XW + i] = __bfloat162float(xb[(((size_t)b * (a.Cin >> 3) + (ci0 >> 3)) * a.x_tstride + t) * 8 + c]);
+        else
+          xs[c * XW + i] = __ldg(xf + ((size_t)b * a.Cin + ci0 + c) * a.x_tstride + t);
       }
       __syncthreads();
       // ---- s = snake(upsample(x)) on the clamped 2x grid
@@ -146,12 +154,14 @@ __global__ void __launch_bounds__(256) k_conv_f32(const ConvArgs a) {
     } else {
       for (int idx = tid; idx < CK * ZW; idx += 256) {
         int c, i;
-        if (TM_IN) { c = idx % CK; i = idx / CK; } else { c = idx / ZW; i = idx % ZW; }
+        if (XL != 0) { c = idx % CK; i = idx / CK; } else { c = idx / ZW; i = idx % ZW; }
         const int m = t0 - hc + i;
         float z = 0.f;
         if (m >= 0 && m < T) {
           if (TM_IN)
             z = ld_dyn(a.x, ((size_t)b * a.Tmax + m) * a.Cin + ci0 + c, a.x_dtype);
+          else if (XL == 2)
+            z = __bfloat162float(xb[(((size_t)b * (a.Cin >> 3) + (ci0 >> 3)) * a.x_tstride + m) * 8 + c]);
           else
             z = __ldg(xf + ((size_t)b * a.Cin + ci0 + c) * a.x_tstride + m);
         }
@@ -211,13 +221,13 @@ __global__ void __launch_bounds__(256) k_conv_f32(const ConvArgs a) {
 // Polyphase: for output n, r=(n+p)%u, q=(n+p)/u: taps kk = r + m*u with j = q - m, m < k/u.
 // ---------------------------------------------------------------------------------------
 struct ConvTrArgs {
-  const float* x;       // [B][Cin][x_tstride]
+  const void* x;        // fp32 [B][Cin][x_tstride]   (BLK: bf16 [B][Cin/8][x_tstride][8])
   int x_tstride;
   const float* wp;      // [Cin][KK][Cout]
   const float* bias;
   const float* bias_b;
   int bias_b_stride;
-  float* out;           // [B][Cout][out_tstride]
+  void* out;            // fp32 [B][Cout][out_tstride] (BLK: bf16 [B][Cout/8][out_tstride][8])
   int out_tstride;
   int Cin, Cout, KK, U;
   const int* lengths;
@@ -225,8 +235,10 @@ struct ConvTrArgs {
   int Tmax_out;
 };
 
-template <int TY, int NC, int NT>
+template <int TY, int NC, int NT, bool BLK>
 __global__ void __launch_bounds__(256) k_convtr_f32(const ConvTrArgs a) {
+  const float* xf = reinterpret_cast<const float*>(a.x);
+  const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(a.x);
   constexpr int TX = 256 / TY;
   constexpr int TT = TX * NT;
   constexpr int COB = TY * NC;
@@ -261,10 +273,14 @@ __global__ void __launch_bounds__(256) k_convtr_f32(const ConvTrArgs a) {
       ws[idx] = (co < a.Cout) ? __ldg(a.wp + ((size_t)ci0 * a.KK + ck) * a.Cout + co) : 0.f;
     }
     for (int idx = tid; idx < CK * QW; idx += 256) {
-      const int c = idx / QW, i = idx % QW;
+      int c, i;
+      if (BLK) { c = idx % CK; i = idx / CK; } else { c = idx / QW; i = idx % QW; }
       const int j = q_lo + i;
-      xs[idx] = (j >= 0 && j < T_in)
-                    ? __ldg(a.x + ((size_t)b * a.Cin + ci0 + c) * a.x_tstride + j) : 0.f;
+      float v = 0.f;
+      if (j >= 0 && j < T_in)
+        v = BLK ? __bfloat162float(xb[(((size_t)b * (a.Cin >> 3) + (ci0 >> 3)) * a.x_tstride + j) * 8 + c])
+                : __ldg(xf + ((size_t)b * a.Cin + ci0 + c) * a.x_tstride + j);
+      xs[c * QW + i] = v;
     }
     __syncthreads();
 #pragma unroll 1
@@ -292,7 +308,21 @@ __global__ void __launch_bounds__(256) k_convtr_f32(const ConvTrArgs a) {
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
       const int n = n0 + tx + TX * i;
-      if (n < T_out) a.out[((size_t)b * a.Cout + co) * a.out_tstride + n] = acc[i][qq] + bsum;
+      if (n >= T_out) continue;
+      if (BLK)
+        reinterpret_cast<__nv_bfloat16*>(a.out)[(((size_t)b * (a.Cout >> 3) + (co >> 3)) * a.out_tstride + n) * 8 + (co & 7)] =
+            __float2bfloat16_rn(acc[i][qq] + bsum);
+      else
+        reinterpret_cast<float*>(a.out)[((size_t)b * a.Cout + co) * a.out_tstride + n] = acc[i][qq] + bsum;
+    }
+  }
+  if (BLK) {
+    // rows [T_out, T_out+32) are zeroed for the consumer's halo reads (ragged batches)
+    for (int idx = tid; idx < COB * 32; idx += 256) {
+      const int co = co0 + idx % COB, n = T_out + idx / COB;
+      if (co < a.Cout && n < a.Tmax_out && n0 + TT >= T_out)
+        reinterpret_cast<__nv_bfloat16*>(a.out)[(((size_t)b * (a.Cout >> 3) + (co >> 3)) * a.out_tstride + n) * 8 + (co & 7)] =
+            __float2bfloat16_rn(0.f);
     }
   }
 }

@@ -52,6 +52,7 @@ struct bvg_plan {
   int cond_off[bvg::kMaxStages + 1];  // [0] = cond_layer, [i+1] = conds[i]
 
   bool weights_loaded = false;
+  void* tc = nullptr;   // bvg::TcPlan (decode_tc.cu)
 
   // grow-only workspace
   void* ws[4] = {nullptr, nullptr, nullptr, nullptr};

@@ -12,6 +12,15 @@ int tc_amp_layer(const float* x, float* y, const float* resid, int B, int C_in, 
                  const float* w, const float* bias, int k, int dilation, int act,
                  const float* up_filter, const float* down_filter, const float* alpha,
                  const float* beta, int logscale, cudaStream_t st);
+// helpers implemented in bvg_api.cu (SIMT kernels reused by the tcgen05 path on the blocked layout)
+int tc_ensure_ws(bvg_plan* p, size_t bytes_per_buf);
+int simt_convtr_blk(bvg_plan* p, const void* x_blk, void* out_blk, int stage, int B, int Tmax, const int* d_len,
+                    cudaStream_t st);
+int simt_post_blk(bvg_plan* p, const void* x_blk, void* wav, int wav_dtype, int B, int Tmax, const int* d_len,
+                  cudaStream_t st);
+void tc_pack_conv_w(const float* w, float* wp, int Cout, int Cin, int K, cudaStream_t st);
+void tc_snake_params(const float* alpha, const float* beta, float* a, float* invb, int C, int logscale,
+                     cudaStream_t st);
 // shared with bvg_api.cu
 int upload_lengths(bvg_plan* p, const int32_t* lengths, int B, int Tmax, cudaStream_t st,
                    const int** d_out);
