@@ -31,23 +31,28 @@ namespace tc {
 
 constexpr int M_TILE = 256;
 constexpr int KC = 32;        // input channels per chunk (4 groups of 8)
-constexpr int XR = 320;       // x rows staged per chunk: t0-32 .. t0+287
+constexpr int XR = 320;       // x rows TMA-staged per chunk: t0-32 .. t0+287
+constexpr int XRA = 344;      // x rows allocated (slack; rows >= XR only ever feed discarded z rows)
 constexpr int X_LEAD = 32;
 constexpr int BOXR = 160;     // TMA box rows (two boxes per channel group)
 constexpr int ZR = 336;       // z rows allocated (16 runs x 21)
-constexpr int NW_ACT = 8;
+constexpr int NW_ACT = 16;    // warps 0-15 activation | 16 x-TMA | 17 weights | 18 MMA | 19 spare | 20-23 epilogue
+constexpr int NX = 3;         // x ring depth
 constexpr int W_STAGES = 4;
 constexpr int W_STAGE_BYTES = 16384;
-constexpr int NTHREADS = (NW_ACT + 3) * 32;
+constexpr int NTHREADS = 768;
+constexpr int MAX_B = 1024;   // utterances per launch (tile-prefix table lives in smem)
 
-constexpr int X_BUF_BYTES = 4 * XR * 16;   // 20480
+constexpr int X_BUF_BYTES = 4 * XRA * 16;  // 22016
+constexpr int X_TX_BYTES = 4 * XR * 16;    // 20480 bytes actually delivered by TMA
 constexpr int Z_BUF_BYTES = 4 * ZR * 16;   // 21504
 constexpr int OFF_X = 0;
-constexpr int OFF_Z = OFF_X + 2 * X_BUF_BYTES;
+constexpr int OFF_Z = OFF_X + NX * X_BUF_BYTES;
 constexpr int OFF_W = OFF_Z + 2 * Z_BUF_BYTES;
 constexpr int OFF_BIAS = OFF_W + W_STAGES * W_STAGE_BYTES;
-constexpr int OFF_BAR = OFF_BIAS + 256 * 4;
-constexpr int NUM_BARS = 2 + 2 + 2 + 2 + 2 * W_STAGES + 1;
+constexpr int OFF_PREFIX = OFF_BIAS + 2 * 256 * 4;
+constexpr int OFF_BAR = OFF_PREFIX + (MAX_B + 8) * 4;
+constexpr int NUM_BARS = 2 * NX + 4 + 2 * W_STAGES + 4;
 constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 
@@ -60,10 +65,15 @@ struct TcArgs {
   const __nv_bfloat16* acc_in; // blocked, or null
   __nv_bfloat16* out;          // blocked [B][Cout/8][Tstride][8]
   float div;
-  int Cin, Cout, K, dil, n_tile, taps_per_stage, tmem_cols;
+  int Cin, Cout, K, dil, n_tile, n_tiles, taps_per_stage;
+  int B;
   int Tstride;                 // rows per (b, channel group) in every activation buffer of this stage
   const int* lengths;
   int rate, Tmax;
+  int lead;                    // ACT=false: rows of x before t0 that tap 0 reads (conv: d(k-1)/2)
+  // ConvTranspose1d mode (up > 0), models.py:157-163: K = taps per phase (k/u), columns are
+  // phase-major n = r*cphase + co, row q = input time, output time = q*up + r - pad.
+  int up, pad, cphase;
   const float* a2;             // [Cin padded to 32]  2*exp(alpha)
   const float* nhb;            // [Cin padded to 32]  -0.5/(exp(beta)+1e-9)
   float up2[12];               // 2*f[k]  (the x2 gain of resample.py:30 folded in)
@@ -177,217 +187,184 @@ __device__ __forceinline__ u64 snake_s_at(const uint32_t* xk, int n, int xlo, in
   return snake_s(y, k);
 }
 
-// One thread: channel pair, L consecutive z rows starting at local row `row0` (global time m0).
+__device__ __forceinline__ u64 shfl64(u64 v, int src) {
+  return ((u64)__shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src) << 32) |
+         (u64)__shfl_sync(0xffffffffu, (uint32_t)v, src);
+}
+
+// One thread: channel pair, L consecutive rows starting at local z row `rowS` (global time m0).
+// It computes its own 2L up-sampled snake samples s'(2*m0 .. 2*m0+2L-1), receives the 5 before /
+// 6 after from the neighbouring runs of the same warp by shuffle (lane -4 / +4), and writes the
+// z rows that fall inside the warp's valid range [vlo, vhi) — the first / last 3 rows of a warp's
+// span lack a neighbour and belong to the adjacent warp's range (spans overlap by 6 rows).
+// Must be entered by all 32 lanes of the warp (EDGE is warp-uniform).
 template <int L, bool EDGE>
-__device__ __forceinline__ void act_run(const uint32_t* __restrict__ xk, uint32_t* __restrict__ zk, int row0,
-                                        int m0, int xlo, int T, const ActCtx& k) {
-  u64 xw[L + 10];
-  u64 sv[2 * L + 10];
-  const int nb = 2 * m0 - 5;
+__device__ __forceinline__ void act_run(const uint32_t* __restrict__ xk, uint32_t* __restrict__ zk, int rowS,
+                                        int vlo, int vhi, int m0, int xlo, int T, const ActCtx& k, int lane) {
+  u64 xw[L + 6];
+  u64 sv[2 * L];
   u64 s_first = 0ull, s_last = 0ull;
   if (EDGE) {
     s_first = snake_s_at(xk, 0, xlo, T, k);
     s_last = snake_s_at(xk, 2 * T - 1, xlo, T, k);
   }
-  auto load_x = [&](int i) {
-    int t = m0 - 5 + i;
+#pragma unroll
+  for (int i = 0; i < L + 6; ++i) {
+    int t = m0 - 3 + i;
     if (EDGE) t = t < 0 ? 0 : (t > T - 1 ? T - 1 : t);
     int r = t - xlo;
-    r = r < 0 ? 0 : (r > XR - 1 ? XR - 1 : r);
-    return bf2_to_f2(xk[r * 4]);
-  };
-  auto make_s = [&](int u) {          // u = n - nb; compile-time after unrolling
+    r = r < 0 ? 0 : (r > XRA - 1 ? XRA - 1 : r);
+    xw[i] = bf2_to_f2(xk[r * 4]);
+  }
+#pragma unroll
+  for (int u = 0; u < 2 * L; ++u) {
     u64 y;
-    if (u & 1) {                       // n even: taps f[11-2i] on x[q-3+i]
-      const int i0 = (u - 1) / 2;
+    if ((u & 1) == 0) {                // n even: taps f[11-2i] on x[q-3+i]
+      const int i0 = u / 2;
       y = mul2(k.upE[0], xw[i0]);
 #pragma unroll
       for (int i = 1; i < 6; ++i) y = fma2(k.upE[i], xw[i0 + i], y);
     } else {                           // n odd: taps f[10-2i] on x[q-2+i]
-      const int i0 = u / 2;
+      const int i0 = (u - 1) / 2 + 1;
       y = mul2(k.upO[0], xw[i0]);
 #pragma unroll
       for (int i = 1; i < 6; ++i) y = fma2(k.upO[i], xw[i0 + i], y);
     }
-    u64 s = snake_s(y, k);
+    u64 sn = snake_s(y, k);
     if (EDGE) {
-      const int n = nb + u;
-      if (n < 0) s = s_first;
-      else if (n > 2 * T - 1) s = s_last;
+      const int n = 2 * m0 + u;
+      if (n < 0) sn = s_first;
+      else if (n > 2 * T - 1) sn = s_last;
     }
-    return s;
-  };
-#pragma unroll
-  for (int i = 0; i < 10; ++i) xw[i] = load_x(i);
-#pragma unroll
-  for (int u = 0; u < 10; ++u) {
-    sv[u] = make_s(u);
+    sv[u] = sn;
   }
+  u64 sb[5], sa[6];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) sb[j] = shfl64(sv[2 * L - 5 + j], (lane + 28) & 31);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) sa[j] = shfl64(sv[j], (lane + 4) & 31);
 #pragma unroll
   for (int r = 0; r < L; ++r) {
-    xw[r + 10] = load_x(r + 10);
-    sv[2 * r + 10] = make_s(2 * r + 10);
-    sv[2 * r + 11] = make_s(2 * r + 11);
     u64 z = k.hb;
 #pragma unroll
-    for (int j = 0; j < 12; ++j) z = fma2(k.dn[j], sv[2 * r + j], z);
+    for (int j = 0; j < 12; ++j) {
+      const int q = 2 * r + j - 5;     // index into this run's own samples
+      const u64 sj = q < 0 ? sb[5 + q] : (q < 2 * L ? sv[q] : sa[q - 2 * L]);
+      z = fma2(k.dn[j], sj, z);
+    }
     float z0, z1;
     upk(z, z0, z1);
-    const int m = m0 + r;
-    if (m < 0 || m >= T) { z0 = 0.f; z1 = 0.f; }      // conv zero padding (utils.py:59)
-    __nv_bfloat162 o = __floats2bfloat162_rn(z0, z1);
-    zk[(row0 + r) * 4] = *reinterpret_cast<uint32_t*>(&o);
+    if (EDGE) {
+      const int m = m0 + r;
+      if (m < 0 || m >= T) { z0 = 0.f; z1 = 0.f; }      // conv zero padding (utils.py:59)
+    }
+    const int row = rowS + r;
+    if (row >= vlo && row < vhi) {
+      __nv_bfloat162 o = __floats2bfloat162_rn(z0, z1);
+      zk[row * 4] = *reinterpret_cast<uint32_t*>(&o);
+    }
   }
 }
 
 // ------------------------------------------------------------------------------ the kernel
+// Persistent: grid = min(#tiles, #SMs); every role walks the same static tile sequence
+// w = blockIdx.x, +gridDim.x, ... (tile = 256 rows x n_tile columns of one utterance; column
+// tile fastest so that CTAs running side by side share x in L2).  The x / z / weight rings and
+// the TMEM accumulator stages keep running across tile boundaries, so the epilogue of tile i,
+// the MMAs of tile i+1 and the activation of tile i+1/i+2 overlap.
+template <int REGS>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
+template <int REGS>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
+
+struct TileCursor {            // monotone walk over the per-utterance tile prefix table
+  const int* prefix;
+  int b = 0;
+  __device__ __forceinline__ void locate(int w, int n_tiles, int& bb, int& t0, int& nt) {
+    const int r = w / n_tiles;
+    nt = w - r * n_tiles;
+    while (r >= prefix[b + 1]) ++b;
+    bb = b;
+    t0 = (r - prefix[b]) * M_TILE;
+  }
+};
+
 template <int L, bool ACT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_amp_tc(const __grid_constant__ CUtensorMap tmx, const TcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.z, nt = blockIdx.y, t0 = blockIdx.x * M_TILE;
-  const int T = a.lengths ? a.lengths[b] * a.rate : a.Tmax;
-  const int n_tile = a.n_tile;
+  const int n_tile = a.n_tile, n_tiles = a.n_tiles;
   const int cg_total = a.Cout >> 3;
-
-  if (t0 >= T) {
-    // one tile of zeros past the end so that un-activated consumers (ConvTranspose1d, plain
-    // convs) see the conv zero padding; tiles further out are never read.
-    if (t0 < T + M_TILE) {
-      const int rows = min(M_TILE, a.Tmax - t0);
-      const int ngrp = min(n_tile >> 3, cg_total - nt * (n_tile >> 3));
-      for (int i = threadIdx.x; i < rows * ngrp; i += NTHREADS) {
-        const int g = i / rows, r = i % rows;
-        uint4* o = reinterpret_cast<uint4*>(
-            a.out + (((size_t)b * cg_total + nt * (n_tile >> 3) + g) * a.Tstride + t0 + r) * 8);
-        *o = make_uint4(0, 0, 0, 0);
-      }
-    }
-    return;
-  }
 
   const uint32_t s_base = smem_u32(smem);
   const uint32_t bar0 = s_base + OFF_BAR;
   auto BAR_XFULL = [&](int i) { return bar0 + 8 * (0 + i); };
-  auto BAR_XEMPTY = [&](int i) { return bar0 + 8 * (2 + i); };
-  auto BAR_ZFULL = [&](int i) { return bar0 + 8 * (4 + i); };
-  auto BAR_ZEMPTY = [&](int i) { return bar0 + 8 * (6 + i); };
-  auto BAR_WFULL = [&](int i) { return bar0 + 8 * (8 + i); };
-  auto BAR_WEMPTY = [&](int i) { return bar0 + 8 * (8 + W_STAGES + i); };
-  const uint32_t BAR_ACC = bar0 + 8 * (8 + 2 * W_STAGES);
+  auto BAR_XEMPTY = [&](int i) { return bar0 + 8 * (NX + i); };
+  auto BAR_ZFULL = [&](int i) { return bar0 + 8 * (2 * NX + i); };
+  auto BAR_ZEMPTY = [&](int i) { return bar0 + 8 * (2 * NX + 2 + i); };
+  auto BAR_WFULL = [&](int i) { return bar0 + 8 * (2 * NX + 4 + i); };
+  auto BAR_WEMPTY = [&](int i) { return bar0 + 8 * (2 * NX + 4 + W_STAGES + i); };
+  auto BAR_ACCFULL = [&](int i) { return bar0 + 8 * (2 * NX + 4 + 2 * W_STAGES + i); };
+  auto BAR_ACCEMPTY = [&](int i) { return bar0 + 8 * (2 * NX + 6 + 2 * W_STAGES + i); };
   float* bias_s = reinterpret_cast<float*>(smem + OFF_BIAS);
+  int* prefix = reinterpret_cast<int*>(smem + OFF_PREFIX);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM);
 
+  const int extra = a.up ? a.K - 1 : 0;      // transposed mode also runs the K-1 rows past the end
   const int hc = a.dil * (a.K - 1) / 2;
   const int NCH = (a.Cin + KC - 1) / KC;
   const int tile_bytes = n_tile * 64;
   const int tps = a.taps_per_stage;
   const int spc = (a.K + tps - 1) / tps;
+  const int nacc = (4 * n_tile <= 512) ? 2 : 1;
 
+  // ---- prologue: tile prefix table, barriers, TMEM
+  if (warp == 0) {
+    int run = 0;
+    for (int b0 = 0; b0 < a.B; b0 += 32) {
+      const int b = b0 + lane;
+      int inc = 0;
+      if (b < a.B) {
+        const int Tin = a.lengths ? a.lengths[b] * a.rate : a.Tmax;
+        inc = (Tin + extra + M_TILE - 1) / M_TILE;
+      }
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+      }
+      if (b < a.B) prefix[b + 1] = run + inc;
+      run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) prefix[0] = 0;
+  }
   if (warp == NW_ACT && lane == 0) {
+    for (int i = 0; i < NX; ++i) { mbar_init(BAR_XFULL(i), 1); mbar_init(BAR_XEMPTY(i), ACT ? NW_ACT : 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(BAR_XFULL(i), 1);
-      mbar_init(BAR_XEMPTY(i), ACT ? NW_ACT : 1);
       mbar_init(BAR_ZFULL(i), NW_ACT);
       mbar_init(BAR_ZEMPTY(i), 1);
+      mbar_init(BAR_ACCFULL(i), 1);
+      mbar_init(BAR_ACCEMPTY(i), 4);
     }
     for (int i = 0; i < W_STAGES; ++i) { mbar_init(BAR_WFULL(i), 1); mbar_init(BAR_WEMPTY(i), 1); }
-    mbar_init(BAR_ACC, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmx)) : "memory");
   }
   if (warp == NW_ACT + 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(s_base + OFF_TMEM), "r"(a.tmem_cols) : "memory");
+                 ::"r"(s_base + OFF_TMEM), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (warp < NW_ACT) {
-    for (int i = threadIdx.x; i < n_tile; i += NW_ACT * 32) {
-      const int co = nt * n_tile + i;
-      float v = 0.f;
-      if (co < a.Cout) {
-        v = __ldg(a.bias + co);
-        if (a.bias_b) v += __ldg(a.bias_b + (size_t)b * a.bias_b_stride + co);
-      }
-      bias_s[i] = v;
-    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  const int total_tiles = prefix[a.B] * n_tiles;
 
-  if (warp == NW_ACT) {
-    // ===================== x producer (TMA) =====================
-    if (lane == 0) {
-      for (int c = 0; c < NCH; ++c) {
-        const int buf = c & 1, use = c >> 1;
-        mbar_wait(BAR_XEMPTY(buf), (use & 1) ^ 1);
-        mbar_expect_tx(BAR_XFULL(buf), X_BUF_BYTES);
-        const uint32_t dst = s_base + OFF_X + buf * X_BUF_BYTES;
-#pragma unroll
-        for (int kg = 0; kg < 4; ++kg)
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-            tma_load_4d(dst + kg * (XR * 16) + h * (BOXR * 16), &tmx, 0, t0 - X_LEAD + h * BOXR, c * 4 + kg, b,
-                        BAR_XFULL(buf));
-      }
-    }
-  } else if (warp == NW_ACT + 1) {
-    // ===================== weight producer (bulk copies) =====================
-    if (lane == 0) {
-      const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wt) + (size_t)nt * NCH * a.K * tile_bytes;
-      int stage = 0, phase = 0;
-      for (int c = 0; c < NCH; ++c)
-        for (int s = 0; s < spc; ++s) {
-          const int taps = min(tps, a.K - s * tps);
-          const uint32_t bytes = (uint32_t)(taps * tile_bytes);
-          mbar_wait(BAR_WEMPTY(stage), phase ^ 1);
-          mbar_expect_tx(BAR_WFULL(stage), bytes);
-          bulk_load(s_base + OFF_W + stage * W_STAGE_BYTES, src, bytes, BAR_WFULL(stage));
-          src += bytes;
-          if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
-        }
-    }
-  } else if (warp == NW_ACT + 2) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, n_tile);
-      const uint32_t lboA = (ACT ? ZR : XR) * 16;
-      const uint32_t lboB = (uint32_t)n_tile * 16;
-      int stage = 0, phase = 0;
-      for (int c = 0; c < NCH; ++c) {
-        const int buf = c & 1, use = c >> 1;
-        mbar_wait(ACT ? BAR_ZFULL(buf) : BAR_XFULL(buf), use & 1);
-        tc_fence_after();
-        const uint32_t abase = ACT ? (s_base + OFF_Z + buf * Z_BUF_BYTES)
-                                   : (s_base + OFF_X + buf * X_BUF_BYTES + (X_LEAD - hc) * 16);
-        for (int s = 0; s < spc; ++s) {
-          const int taps = min(tps, a.K - s * tps);
-          mbar_wait(BAR_WFULL(stage), phase);
-          tc_fence_after();
-          const uint32_t wbase = s_base + OFF_W + stage * W_STAGE_BYTES;
-          for (int tj = 0; tj < taps; ++tj) {
-            const int j = s * tps + tj;
-#pragma unroll
-            for (int mb = 0; mb < 2; ++mb)
-#pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
-                const u64 ad = make_sdesc(abase + (mb * 128 + j * a.dil) * 16 + ks * 2 * lboA, lboA, 128);
-                const u64 bd = make_sdesc(wbase + tj * tile_bytes + ks * 2 * lboB, lboB, 128);
-                umma_bf16(tmem + mb * n_tile, ad, bd, idesc, (c | j | ks) != 0);
-              }
-          }
-          umma_commit(BAR_WEMPTY(stage));          // weight stage free once these MMAs retire
-          if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
-        }
-        umma_commit(ACT ? BAR_ZEMPTY(buf) : BAR_XEMPTY(buf));
-      }
-      umma_commit(BAR_ACC);
-    }
-  } else {
-    // ===================== activation warps, then epilogue =====================
+  if (warp < NW_ACT) {
+    // ===================== activation warps =====================
+    reg_inc<96>();
     if (ACT) {
       ActCtx k;
 #pragma unroll
@@ -397,96 +374,287 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const TcArgs a) {
       }
 #pragma unroll
       for (int i = 0; i < 12; ++i) k.dn[i] = pk(a.dn[i], a.dn[i]);
-      const int kg = warp & 3, half = warp >> 2, g = lane >> 2, p = lane & 3;
-      const int row0 = (half * 8 + g) * L;
+      // 4 channel groups x 4 warps; a warp's 8 runs of L rows span 8L rows and yield V = 8L-6 z rows
+      constexpr int V = 8 * L - 6;
+      const int kg = warp & 3, wq = warp >> 2, g = lane >> 2, p = lane & 3;
       const int ZW = M_TILE + 2 * hc;
-      const int m0 = t0 - hc + row0;
-      const int xlo = t0 - X_LEAD;
-      // runs whose x window [m0-5, m0+L+4] leaves [0, T) need the replicate clamps
-      const bool edge = (m0 - 5 < 0) || (m0 + L + 4 > T - 1);
-      for (int c = 0; c < NCH; ++c) {
-        const int buf = c & 1, use = c >> 1;
-        const int ch = c * KC + kg * 8 + 2 * p;
-        const float2 a2v = __ldg(reinterpret_cast<const float2*>(a.a2 + ch));
-        const float2 nhbv = __ldg(reinterpret_cast<const float2*>(a.nhb + ch));
-        k.a2 = pk(a2v.x, a2v.y);
-        k.nhb = pk(nhbv.x, nhbv.y);
-        k.hb = pk(-nhbv.x, -nhbv.y);
-        mbar_wait(BAR_XFULL(buf), use & 1);
-        mbar_wait(BAR_ZEMPTY(buf), (use & 1) ^ 1);
-        if (row0 < ZW) {
-          const uint32_t* xk = reinterpret_cast<const uint32_t*>(smem + OFF_X + buf * X_BUF_BYTES) + kg * (XR * 4) + p;
-          uint32_t* zk = reinterpret_cast<uint32_t*>(smem + OFF_Z + buf * Z_BUF_BYTES) + kg * (ZR * 4) + p;
-          if (edge) act_run<L, true>(xk, zk, row0, m0, xlo, T, k);
-          else act_run<L, false>(xk, zk, row0, m0, xlo, T, k);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // z stores -> async proxy (UMMA)
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(BAR_ZFULL(buf));
-          mbar_arrive(BAR_XEMPTY(buf));
+      const int vlo = wq * V, vhi = min(vlo + V, ZR);
+      const int rowS = vlo - 3 + g * L;
+      TileCursor cur{prefix};
+      int gi = 0;
+      for (int w = blockIdx.x; w < total_tiles; w += gridDim.x) {
+        int b, t0, nt;
+        cur.locate(w, n_tiles, b, t0, nt);
+        const int T = a.lengths ? a.lengths[b] * a.rate : a.Tmax;
+        const int m0 = t0 - hc + rowS;
+        const int xlo = t0 - X_LEAD;
+        // runs whose x window [m0-3, m0+L+2] leaves [0, T) need the replicate clamps (warp-uniform
+        // because the run takes part in shuffles)
+        const bool edge = __any_sync(0xffffffffu, (m0 - 3 < 0) || (m0 + L + 2 > T - 1));
+        for (int c = 0; c < NCH; ++c, ++gi) {
+          const int xb = gi % NX, xuse = gi / NX, zb = gi & 1, zuse = gi >> 1;
+          const int ch = c * KC + kg * 8 + 2 * p;
+          const float2 a2v = __ldg(reinterpret_cast<const float2*>(a.a2 + ch));
+          const float2 nhbv = __ldg(reinterpret_cast<const float2*>(a.nhb + ch));
+          k.a2 = pk(a2v.x, a2v.y);
+          k.nhb = pk(nhbv.x, nhbv.y);
+          k.hb = pk(-nhbv.x, -nhbv.y);
+          mbar_wait(BAR_XFULL(xb), xuse & 1);
+          mbar_wait(BAR_ZEMPTY(zb), (zuse & 1) ^ 1);
+          if (vlo < ZW) {
+            const uint32_t* xk = reinterpret_cast<const uint32_t*>(smem + OFF_X + xb * X_BUF_BYTES) + kg * (XRA * 4) + p;
+            uint32_t* zk = reinterpret_cast<uint32_t*>(smem + OFF_Z + zb * Z_BUF_BYTES) + kg * (ZR * 4) + p;
+            if (edge) act_run<L, true>(xk, zk, rowS, vlo, vhi, m0, xlo, T, k, lane);
+            else act_run<L, false>(xk, zk, rowS, vlo, vhi, m0, xlo, T, k, lane);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // z stores -> async proxy (UMMA)
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(BAR_ZFULL(zb));
+            mbar_arrive(BAR_XEMPTY(xb));
+          }
         }
       }
     }
-    // ---- epilogue: TMEM -> registers -> (+bias, +resid, +running sum, /div) -> bf16 -> HBM
-    mbar_wait(BAR_ACC, 0);
-    tc_fence_after();
-    const int q = warp & 3, h = warp >> 2;
-    const int t = t0 + h * 128 + q * 32 + lane;
-    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * n_tile);
-    for (int c0 = 0; c0 < n_tile; c0 += 16) {
-      uint32_t v[16];
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-          : "r"(taddr + c0));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  } else if (warp < NW_ACT + 4) {
+    reg_dec<32>();
+    if (warp == NW_ACT) {
+      // ===================== x producer (TMA) =====================
+      if (lane == 0) {
+        TileCursor cur{prefix};
+        int gi = 0;
+        for (int w = blockIdx.x; w < total_tiles; w += gridDim.x) {
+          int b, t0, nt;
+          cur.locate(w, n_tiles, b, t0, nt);
+          for (int c = 0; c < NCH; ++c, ++gi) {
+            const int xb = gi % NX, xuse = gi / NX;
+            mbar_wait(BAR_XEMPTY(xb), (xuse & 1) ^ 1);
+            mbar_expect_tx(BAR_XFULL(xb), X_TX_BYTES);
+            const uint32_t dst = s_base + OFF_X + xb * X_BUF_BYTES;
 #pragma unroll
-      for (int kk = 0; kk < 2; ++kk) {
-        const int cg = nt * (n_tile >> 3) + (c0 >> 3) + kk;       // global channel group
-        if (cg >= cg_total || t >= a.Tmax) continue;
-        const size_t idx = (((size_t)b * cg_total + cg) * a.Tstride + t) * 8;
-        uint4 o = make_uint4(0, 0, 0, 0);
-        if (t < T) {
-          float f[8];
+            for (int kg = 0; kg < 4; ++kg)
 #pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[kk * 8 + e]) + bias_s[c0 + kk * 8 + e];
-          if (a.resid) {
-            const uint4 r = *reinterpret_cast<const uint4*>(a.resid + idx);
-            const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              f[2 * e] += __uint_as_float(rw[e] << 16);
-              f[2 * e + 1] += __uint_as_float(rw[e] & 0xffff0000u);
-            }
+              for (int h = 0; h < 2; ++h)
+                tma_load_4d(dst + kg * (XRA * 16) + h * (BOXR * 16), &tmx, 0, t0 - X_LEAD + h * BOXR, c * 4 + kg, b,
+                            BAR_XFULL(xb));
           }
-          if (a.acc_in) {
-            const uint4 r = *reinterpret_cast<const uint4*>(a.acc_in + idx);
-            const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              f[2 * e] += __uint_as_float(rw[e] << 16);
-              f[2 * e + 1] += __uint_as_float(rw[e] & 0xffff0000u);
-            }
-          }
-          if (a.div != 1.0f) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = f[e] / a.div;
-          }
-          __nv_bfloat162 p0 = __floats2bfloat162_rn(f[0], f[1]), p1 = __floats2bfloat162_rn(f[2], f[3]);
-          __nv_bfloat162 p2 = __floats2bfloat162_rn(f[4], f[5]), p3 = __floats2bfloat162_rn(f[6], f[7]);
-          o = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
-                         *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
         }
-        *reinterpret_cast<uint4*>(a.out + idx) = o;
+      }
+    } else if (warp == NW_ACT + 1) {
+      // ===================== weight producer (bulk copies) =====================
+      if (lane == 0) {
+        int stage = 0, phase = 0;
+        for (int w = blockIdx.x; w < total_tiles; w += gridDim.x) {
+          const int nt = w % n_tiles;
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wt) + (size_t)nt * NCH * a.K * tile_bytes;
+          for (int c = 0; c < NCH; ++c)
+            for (int s = 0; s < spc; ++s) {
+              const int taps = min(tps, a.K - s * tps);
+              const uint32_t bytes = (uint32_t)(taps * tile_bytes);
+              mbar_wait(BAR_WEMPTY(stage), phase ^ 1);
+              mbar_expect_tx(BAR_WFULL(stage), bytes);
+              bulk_load(s_base + OFF_W + stage * W_STAGE_BYTES, src, bytes, BAR_WFULL(stage));
+              src += bytes;
+              if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+      }
+    } else if (warp == NW_ACT + 2) {
+      // ===================== MMA issuer =====================
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc_bf16(128, n_tile);
+        const uint32_t lboA = (ACT ? ZR : XRA) * 16;
+        const uint32_t lboB = (uint32_t)n_tile * 16;
+        // descriptor = constant high part | (smem address >> 4); taps / M blocks / K steps only
+        // move the 14-bit address field (rows are 16 B apart: +1 unit = +1 time sample)
+        const u64 hiA = make_sdesc(0, lboA, 128), hiB = make_sdesc(0, lboB, 128);
+        const uint32_t ksA = 2 * lboA / 16, ksB = 2 * lboB / 16, tileU = (uint32_t)tile_bytes / 16;
+        int stage = 0, phase = 0, gi = 0, it = 0;
+        for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++it) {
+          const int as = (nacc == 2) ? (it & 1) : 0;
+          const int ause = (nacc == 2) ? (it >> 1) : it;
+          mbar_wait(BAR_ACCEMPTY(as), (ause & 1) ^ 1);       // epilogue has drained this accumulator stage
+          tc_fence_after();
+          const uint32_t tm = tmem + (uint32_t)(as * 2 * n_tile);
+          uint32_t accflag = 0;
+          for (int c = 0; c < NCH; ++c, ++gi) {
+            const int xb = gi % NX, xuse = gi / NX, zb = gi & 1, zuse = gi >> 1;
+            if (ACT) mbar_wait(BAR_ZFULL(zb), zuse & 1);
+            else mbar_wait(BAR_XFULL(xb), xuse & 1);
+            tc_fence_after();
+            const uint32_t aU = (ACT ? (s_base + OFF_Z + zb * Z_BUF_BYTES)
+                                     : (s_base + OFF_X + xb * X_BUF_BYTES + (X_LEAD - a.lead) * 16)) >> 4;
+            for (int s = 0; s < spc; ++s) {
+              const int taps = min(tps, a.K - s * tps);
+              mbar_wait(BAR_WFULL(stage), phase);
+              tc_fence_after();
+              const uint32_t wU = (s_base + OFF_W + stage * W_STAGE_BYTES) >> 4;
+              for (int tj = 0; tj < taps; ++tj) {
+                const uint32_t a0 = aU + (uint32_t)((s * tps + tj) * a.dil);
+                const uint32_t b0 = wU + (uint32_t)tj * tileU;
+                umma_bf16(tm, hiA | a0, hiB | b0, idesc, accflag);
+                umma_bf16(tm, hiA | (a0 + ksA), hiB | (b0 + ksB), idesc, 1u);
+                umma_bf16(tm + n_tile, hiA | (a0 + 128), hiB | b0, idesc, accflag);
+                umma_bf16(tm + n_tile, hiA | (a0 + 128 + ksA), hiB | (b0 + ksB), idesc, 1u);
+                accflag = 1u;
+              }
+              umma_commit(BAR_WEMPTY(stage));          // weight stage free once these MMAs retire
+              if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(ACT ? BAR_ZEMPTY(zb) : BAR_XEMPTY(xb));
+          }
+          umma_commit(BAR_ACCFULL(as));
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps: TMEM -> (+bias, +resid, +sum, /div) -> bf16 -> HBM ====
+    reg_dec<64>();
+    const int q = warp & 3;
+    const int etid = threadIdx.x - (NW_ACT + 4) * 32;   // 0..127
+    TileCursor cur{prefix};
+    int it = 0;
+    for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++it) {
+      int b, t0, nt;
+      cur.locate(w, n_tiles, b, t0, nt);
+      const int Tin = a.lengths ? a.lengths[b] * a.rate : a.Tmax;
+      const int T = Tin + extra;
+      const int as = (nacc == 2) ? (it & 1) : 0;
+      const int ause = (nacc == 2) ? (it >> 1) : it;
+      float* bs = bias_s + as * 256;
+      asm volatile("bar.sync 1, 128;" ::: "memory");     // previous user of bias_s[as] is done
+      for (int i = etid; i < n_tile; i += 128) {
+        int co = nt * n_tile + i;
+        float v = 0.f;
+        if (co < a.Cout) {
+          if (a.up) co %= a.cphase;
+          v = __ldg(a.bias + co);
+          if (a.bias_b) v += __ldg(a.bias_b + (size_t)b * a.bias_b_stride + co);
+        }
+        bs[i] = v;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if ((a.resid || a.acc_in) && a.up == 0) {
+        // warm L2 with this tile's residual / running-sum rows while its MMAs are still running
+        const int ng = min(n_tile >> 3, cg_total - nt * (n_tile >> 3));
+        for (int mb = 0; mb < 2; ++mb) {
+          const int t = t0 + mb * 128 + q * 32 + lane;
+          if (t >= T) continue;
+          for (int g = 0; g < ng; ++g) {
+            const size_t ii = (((size_t)b * cg_total + nt * (n_tile >> 3) + g) * a.Tstride + t) * 8;
+            if (a.resid) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.resid + ii));
+            if (a.acc_in) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.acc_in + ii));
+          }
+        }
+      }
+      mbar_wait(BAR_ACCFULL(as), ause & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * n_tile);
+      const int gpp = a.up ? (a.cphase >> 3) : cg_total;               // channel groups per output row set
+      const size_t ubase = (size_t)b * gpp * a.Tstride * 8;            // this utterance's block
+      const __nv_bfloat16* resid = a.resid ? a.resid + ubase : nullptr;
+      const __nv_bfloat16* accin = a.acc_in ? a.acc_in + ubase : nullptr;
+      __nv_bfloat16* outp = a.out + ubase;
+#pragma unroll 1
+      for (int mb = 0; mb < 2; ++mb) {
+        const int t = t0 + mb * 128 + q * 32 + lane;
+#pragma unroll 1
+        for (int cb0 = 0; cb0 < n_tile; cb0 += 32) {
+          const int ngrp = min(4, (n_tile - cb0) >> 3);          // channel groups in this column block
+          // 1) element offset / liveness per group, then the residual / running-sum loads
+          //    off >= 0: live; -1: skip; <= -2: store zeros at -(off+2)
+          int off[4];
+          uint4 rr[4], qq[4];
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            off[kk] = -1;
+            rr[kk] = make_uint4(0, 0, 0, 0);
+            qq[kk] = make_uint4(0, 0, 0, 0);
+            const int cgn = nt * (n_tile >> 3) + (cb0 >> 3) + kk;
+            if (kk >= ngrp || cgn >= cg_total) continue;
+            if (a.up) {                                          // phase scatter of ConvTranspose1d
+              const int r = cgn / gpp, cg = cgn - r * gpp;
+              const int to = t * a.up + r - a.pad;
+              if (t >= T || to < 0 || to >= Tin * a.up) continue;
+              off[kk] = (cg * a.Tstride + to) * 8;
+            } else {
+              if (t >= a.Tmax) continue;
+              const int o = (cgn * a.Tstride + t) * 8;
+              off[kk] = (t < T) ? o : -2 - o;
+            }
+            if (off[kk] >= 0) {
+              if (resid) rr[kk] = *reinterpret_cast<const uint4*>(resid + off[kk]);
+              if (accin) qq[kk] = *reinterpret_cast<const uint4*>(accin + off[kk]);
+            }
+          }
+          // 2) accumulators, 16 columns at a time
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            if (hh * 2 >= ngrp) continue;                        // warp-uniform
+            uint32_t v[16];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                : "r"(taddr + (uint32_t)(mb * n_tile + cb0 + hh * 16)));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int k2 = 0; k2 < 2; ++k2) {
+              const int kk = hh * 2 + k2;
+              const int ox = off[kk];
+              if (ox == -1) continue;
+              uint4 o = make_uint4(0, 0, 0, 0);
+              if (ox >= 0) {
+                float f[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[k2 * 8 + e]) + bs[cb0 + kk * 8 + e];
+                const uint32_t rw[4] = {rr[kk].x, rr[kk].y, rr[kk].z, rr[kk].w};
+                const uint32_t qw[4] = {qq[kk].x, qq[kk].y, qq[kk].z, qq[kk].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {        // zero words when there is no residual / running sum
+                  f[2 * e] += __uint_as_float(rw[e] << 16);
+                  f[2 * e + 1] += __uint_as_float(rw[e] & 0xffff0000u);
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  f[2 * e] += __uint_as_float(qw[e] << 16);
+                  f[2 * e + 1] += __uint_as_float(qw[e] & 0xffff0000u);
+                }
+                if (a.div != 1.0f) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) f[e] = f[e] / a.div;
+                }
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(f[0], f[1]), p1 = __floats2bfloat162_rn(f[2], f[3]);
+                __nv_bfloat162 p2 = __floats2bfloat162_rn(f[4], f[5]), p3 = __floats2bfloat162_rn(f[6], f[7]);
+                o = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                               *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+              }
+              *reinterpret_cast<uint4*>(outp + (ox >= 0 ? ox : -(ox + 2))) = o;
+            }
+          }
+        }
+      }
+      // accumulator stage can be overwritten by the MMAs of tile it + nacc
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR_ACCEMPTY(as));
+      // un-activated consumers (ConvTranspose1d) read one row past the end: keep rows [T, T+8) zero
+      // when the utterance ends exactly on this tile's boundary (otherwise they were zeroed above)
+      if (a.up == 0 && T == t0 + M_TILE && T < a.Tmax && q == 0) {
+        const int ngr = min(n_tile >> 3, cg_total - nt * (n_tile >> 3));
+        for (int i = lane; i < ngr * 8; i += 32) {
+          const int g = i >> 3, r = T + (i & 7);
+          if (r < a.Tmax)
+            *reinterpret_cast<uint4*>(a.out + (((size_t)b * cg_total + nt * (n_tile >> 3) + g) * a.Tstride + r) * 8) =
+                make_uint4(0, 0, 0, 0);
+        }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == NW_ACT + 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(a.tmem_cols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
   }
 }
 

@@ -33,6 +33,32 @@ __global__ void k_pack_wt(const float* __restrict__ wp, __nv_bfloat16* __restric
   }
 }
 
+// ConvTranspose1d weights [Cin][KK][Cout] (tap-major fp32) -> bf16 tiles for the 2-tap implicit GEMM:
+// column n = r*Cout + co (phase-major), tap j reads x[q-(M-1-j)] with kernel index kk = r + (M-1-j)*u
+__global__ void k_pack_wt_tr(const float* __restrict__ wp, __nv_bfloat16* __restrict__ wt, int Cin, int Cout,
+                             int KK, int U, int n_tile, int NCH, int NT) {
+  const int M = KK / U;
+  const size_t total = (size_t)NT * NCH * M * 32 * n_tile;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int e = idx % 8;
+    size_t r0 = idx / 8;
+    const int n = r0 % n_tile; r0 /= n_tile;
+    const int kg = r0 % 4; r0 /= 4;
+    const int j = r0 % M; r0 /= M;
+    const int c = r0 % NCH;
+    const int nt = r0 / NCH;
+    const int col = nt * n_tile + n, ci = c * 32 + kg * 8 + e;
+    float v = 0.f;
+    if (col < U * Cout && ci < Cin) {
+      const int r = col / Cout, co = col % Cout;
+      const int kk = r + (M - 1 - j) * U;
+      v = wp[((size_t)ci * KK + kk) * Cout + co];
+    }
+    wt[idx] = __float2bfloat16_rn(v);
+  }
+}
+
 // a2 = 2*exp(alpha), nhb = -0.5/(exp(beta)+1e-9), zero-padded to a multiple of 32 channels
 __global__ void k_tc_params(const float* a, const float* invb, float* a2, float* nhb, int C, int Cpad) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -86,6 +112,7 @@ struct TcLayer {
 
 struct TcPlan {
   TcLayer pre;
+  TcLayer ups[kMaxStages];
   TcLayer rb1[kMaxBlocks][BVG_MAX_DIL], rb2[kMaxBlocks][BVG_MAX_DIL];
   void* lat_blk = nullptr;
   size_t lat_bytes = 0;
@@ -141,11 +168,31 @@ static int build_layer(std::vector<void*>& owned, TcLayer& L, const ConvW& cw, c
   return 0;
 }
 
+// ConvTranspose1d(Cin, Cout, KK, stride U) as an implicit GEMM with M = KK/U taps and U*Cout columns
+static int build_layer_tr(std::vector<void*>& owned, TcLayer& L, const ConvW& cw, int U, cudaStream_t st) {
+  const int M = cw.K / U, ncols = U * cw.Cout;
+  pick_tile(ncols, &L.n_tile, &L.n_tiles);
+  L.nch = (cw.Cin + KC - 1) / KC;
+  L.tps = std::max(1, std::min(M, W_STAGE_BYTES / (L.n_tile * 64)));
+  L.tmem_cols = pow2_cols(2 * L.n_tile);
+  const size_t elems = (size_t)L.n_tiles * L.nch * M * 32 * L.n_tile;
+  if (!L.wt) {
+    BVG_CUDA(cudaMalloc((void**)&L.wt, elems * sizeof(__nv_bfloat16)));
+    owned.push_back(L.wt);
+  }
+  k_pack_wt_tr<<<(int)std::min<size_t>((elems + 255) / 256, 8192), 256, 0, st>>>(cw.wp, L.wt, cw.Cin, cw.Cout, cw.K, U,
+                                                                                L.n_tile, L.nch, L.n_tiles);
+  BVG_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int tc_plan_pack(bvg_plan* p, cudaStream_t st) {
   if (!p->tc) p->tc = new TcPlan();
   TcPlan* t = static_cast<TcPlan*>(p->tc);
   int rc;
   if ((rc = build_layer(t->owned, t->pre, p->conv_pre, nullptr, st))) return rc;
+  for (int i = 0; i < p->n_stages; ++i)
+    if ((rc = build_layer_tr(t->owned, t->ups[i], p->ups[i], p->cfg.upsample_rates[i], st))) return rc;
   for (int i = 0; i < p->n_stages; ++i)
     for (int j = 0; j < p->cfg.num_kernels; ++j) {
       const int n = i * p->cfg.num_kernels + j;
@@ -233,6 +280,10 @@ struct TcLaunch {
   int B = 1, Tstride = 0, rate = 1;
   const int* d_len = nullptr;
   int cls = 0;
+  const int32_t* h_len = nullptr;   // host copy of the lengths (grid sizing)
+  int sm_count = 0;
+  int up = 0, pad = 0, cphase = 0;   // ConvTranspose1d mode
+  int out_tstride = 0;               // defaults to Tstride
 };
 
 template <int L, bool ACT>
@@ -254,23 +305,35 @@ static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, cons
   a.wt = L.wt; a.bias = cw.bias; a.bias_b = q.bias_b; a.bias_b_stride = q.bias_b_stride;
   a.resid = q.resid; a.acc_in = q.acc_in; a.out = q.out; a.div = q.div;
   a.Cin = cw.Cin; a.Cout = cw.Cout; a.K = cw.K; a.dil = q.dil;
-  a.n_tile = L.n_tile; a.taps_per_stage = L.tps; a.tmem_cols = L.tmem_cols;
-  a.Tstride = q.Tstride; a.lengths = q.d_len; a.rate = q.rate; a.Tmax = q.Tstride;
+  a.n_tile = L.n_tile; a.n_tiles = L.n_tiles; a.taps_per_stage = L.tps; a.B = q.B;
+  a.Tstride = q.out_tstride ? q.out_tstride : q.Tstride;
+  a.lengths = q.d_len; a.rate = q.rate; a.Tmax = q.Tstride;
+  a.up = q.up; a.pad = q.pad; a.cphase = q.cphase;
   const int hc = q.dil * (cw.K - 1) / 2;
+  a.lead = q.up ? cw.K - 1 : hc;
   if (aw) {
     a.a2 = L.a2; a.nhb = L.nhb;
     for (int i = 0; i < 12; ++i) { a.up2[i] = 2.0f * aw->up[i]; a.dn[i] = aw->dn[i]; }
   }
-  dim3 grid(ceil_div(q.Tstride, M_TILE), L.n_tiles, q.B);
+  if (q.B > MAX_B) return fail(BVG_ERR_UNSUPPORTED, "tcgen05 path: at most %d utterances per launch", MAX_B);
+  // persistent grid: one CTA per SM walking the (utterance, time tile, column tile) sequence
+  const int extra = q.up ? cw.K - 1 : 0;
+  long long tiles = 0;
+  for (int b = 0; b < q.B; ++b) {
+    const long long Tb = (q.h_len ? (long long)q.h_len[b] * q.rate : q.Tstride) + extra;
+    tiles += (Tb + M_TILE - 1) / M_TILE;
+  }
+  tiles *= L.n_tiles;
+  dim3 grid((unsigned)std::min<long long>(tiles, q.sm_count > 0 ? q.sm_count : 148));
   const double samples = (p ? p->cur_sum_frames : 0.0) * q.rate;
   prof_begin(p, st, q.cls, 2.0 * cw.Cin * cw.Cout * cw.K * samples,
              samples * 2.0 * (cw.Cin + cw.Cout + (q.resid ? cw.Cout : 0) + (q.acc_in ? cw.Cout : 0)) +
                  2.0 * cw.Cin * cw.Cout * cw.K);
   int rc;
-  if (!aw) rc = launch_inst<17, false>(map, a, grid, st);
-  else if (hc <= 8) rc = launch_inst<17, true>(map, a, grid, st);
-  else if (hc <= 24) rc = launch_inst<19, true>(map, a, grid, st);
-  else rc = launch_inst<21, true>(map, a, grid, st);
+  // run length per activation thread: 4 warps x (8L - 6) valid rows must cover 256 + 2*hc z rows
+  if (!aw) rc = launch_inst<9, false>(map, a, grid, st);
+  else if (hc <= 4) rc = launch_inst<9, true>(map, a, grid, st);
+  else rc = launch_inst<11, true>(map, a, grid, st);
   prof_end(p, st);
   if (p) ++p->last_launches;
   return rc;
@@ -279,7 +342,6 @@ static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, cons
 // ------------------------------------------------------------------------------ decode
 int tc_decode(bvg_plan* p, const void* latent, int latent_dtype, const int32_t* h_len, const int* d_len, int B,
               int Tmax, void* wav_out, int wav_dtype, cudaStream_t st) {
-  (void)h_len;
   TcPlan* t = static_cast<TcPlan*>(p->tc);
   if (!t) return fail(BVG_ERR_STATE, "tcgen05 path: weights not packed");
   int rc;
@@ -316,6 +378,7 @@ int tc_decode(bvg_plan* p, const void* latent, int latent_dtype, const int32_t* 
     TcLaunch q;
     q.x = t->lat_blk; q.out = cur; q.bias_b = p->condb + p->cond_off[0]; q.bias_b_stride = p->cond_total;
     q.dil = 1; q.B = B; q.Tstride = Tmax; q.rate = 1; q.d_len = d_len; q.cls = 2;
+    q.h_len = h_len; q.sm_count = p->sm_count;
     if ((rc = launch_tc(p, *map, t->pre, p->conv_pre, nullptr, q, st))) return rc;
   }
   const int nk = p->cfg.num_kernels;
@@ -326,7 +389,20 @@ int tc_decode(bvg_plan* p, const void* latent, int latent_dtype, const int32_t* 
     for (int qd = 0; qd < 4; ++qd)
       if (bufs[qd] != cur) free3[nf++] = bufs[qd];
     __nv_bfloat16 *xin = free3[0], *xr = free3[1], *xt = free3[2], *xs = cur;
-    if ((rc = simt_convtr_blk(p, cur, xin, i, B, Tmax, d_len, st))) return rc;
+    {
+      // ConvTranspose1d + cond add (models.py:232-236) as a (k/u)-tap implicit GEMM on the input rate
+      const int U = p->cfg.upsample_rates[i], KK = p->ups[i].K, Tin = Tmax * p->rate[i];
+      ConvW cw = p->ups[i];
+      cw.Cout = U * Ci; cw.K = KK / U;
+      TcLaunch qu;
+      qu.x = cur; qu.out = xin; qu.dil = 1; qu.B = B; qu.Tstride = Tin; qu.out_tstride = Ti; qu.rate = p->rate[i];
+      qu.d_len = d_len; qu.cls = 2; qu.up = U; qu.pad = (KK - U) / 2; qu.cphase = Ci;
+      qu.h_len = h_len; qu.sm_count = p->sm_count;
+      qu.bias_b = p->cfg.cond_in_each_up_layer ? p->condb + p->cond_off[i + 1] : nullptr;
+      qu.bias_b_stride = p->cond_total;
+      if ((rc = get_map(t, cur, p->C[i], Tin, B, &map))) return rc;
+      if ((rc = launch_tc(p, *map, t->ups[i], cw, nullptr, qu, st))) return rc;
+    }
     const int cls = (Ci >= 192) ? 0 : 1;
     for (int j = 0; j < nk; ++j) {
       const int n = i * nk + j;
@@ -335,12 +411,14 @@ int tc_decode(bvg_plan* p, const void* latent, int latent_dtype, const int32_t* 
         const int d = p->cfg.resblock_dilation_sizes[j][m];
         TcLaunch qa;
         qa.x = xcur; qa.out = xt; qa.dil = d; qa.B = B; qa.Tstride = Ti; qa.rate = Ri; qa.d_len = d_len; qa.cls = cls;
+        qa.h_len = h_len; qa.sm_count = p->sm_count;
         if ((rc = get_map(t, xcur, Ci, Ti, B, &map))) return rc;
         if ((rc = launch_tc(p, *map, t->rb1[n][m], p->rb1[n][m], &p->rba[n][2 * m], qa, st))) return rc;
 
         const bool last = (m == BVG_MAX_DIL - 1);
         TcLaunch qb;
         qb.x = xt; qb.resid = xcur; qb.dil = 1; qb.B = B; qb.Tstride = Ti; qb.rate = Ri; qb.d_len = d_len; qb.cls = cls;
+        qb.h_len = h_len; qb.sm_count = p->sm_count;
         if (!last) {
           qb.out = xr;
         } else {
@@ -403,6 +481,12 @@ int tc_amp_layer(const float* x, float* y, const float* resid, int B, int C_in, 
   if ((rc = make_map(xb, C_in, T, B, &map))) { cleanup(); return rc; }
   TcLaunch q;
   q.x = xb; q.resid = rb; q.out = yb; q.dil = dilation; q.B = B; q.Tstride = T; q.rate = 1; q.d_len = nullptr;
+  {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    q.sm_count = sms;
+  }
   rc = launch_tc(nullptr, map, L, cw, act ? &aw : nullptr, q, st);
   if (!rc) {
     dim3 g3(ceil_div(T, 128), C_out / 8, B);
