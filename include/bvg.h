@@ -142,7 +142,9 @@ int64_t bvg_plan_workspace_bytes(const bvg_plan* plan);
 int bvg_plan_last_launches(const bvg_plan* plan);
 
 /* Optional per-launch device timing (CUDA events on the caller's stream around every kernel of
- * a decode), accumulated per class until read.  Classes: 0 = fused AMP layers of the
+ * a decode), accumulated per class until read.  While it is on, the three AMP blocks of a stage,
+ * which normally run on three streams, are serialised on the caller's stream so that each
+ * event pair brackets exactly one kernel.  Classes: 0 = fused AMP layers of the
  * tensor-bound stages (C >= 192), 1 = fused AMP layers of the small-channel stages, 2 =
  * conv_pre / ConvTranspose1d / cond, 3 = activation_post + conv_post + tanh. */
 #define BVG_PROFILE_CLASSES 4

@@ -32,7 +32,7 @@ namespace tc {
 constexpr int M_TILE = 256;
 constexpr int KC = 32;        // input channels per chunk (4 groups of 8)
 constexpr int XR = 320;       // x rows TMA-staged per chunk: t0-32 .. t0+287
-constexpr int XRA = 344;      // x rows allocated (slack; rows >= XR only ever feed discarded z rows)
+constexpr int XRA = 368;      // x rows allocated (slack; rows >= XR only ever feed discarded z rows)
 constexpr int X_LEAD = 32;
 constexpr int BOXR = 160;     // TMA box rows (two boxes per channel group)
 constexpr int ZR = 336;       // z rows allocated (16 runs x 21)
@@ -200,7 +200,7 @@ __device__ __forceinline__ u64 shfl64(u64 v, int src) {
 // Must be entered by all 32 lanes of the warp (EDGE is warp-uniform).
 template <int L, bool EDGE>
 __device__ __forceinline__ void act_run(const uint32_t* __restrict__ xk, uint32_t* __restrict__ zk, int rowS,
-                                        int vlo, int vhi, int m0, int xlo, int T, const ActCtx& k, int lane) {
+                                        uint32_t smask, int m0, int xlo, int T, const ActCtx& k, int lane) {
   u64 xw[L + 6];
   u64 sv[2 * L];
   u64 s_first = 0ull, s_last = 0ull;
@@ -213,7 +213,7 @@ __device__ __forceinline__ void act_run(const uint32_t* __restrict__ xk, uint32_
     int t = m0 - 3 + i;
     if (EDGE) t = t < 0 ? 0 : (t > T - 1 ? T - 1 : t);
     int r = t - xlo;
-    r = r < 0 ? 0 : (r > XRA - 1 ? XRA - 1 : r);
+    if (EDGE) r = r < 0 ? 0 : (r > XRA - 1 ? XRA - 1 : r);   // interior runs: 1 <= r <= 8L*4+35 < XRA
     xw[i] = bf2_to_f2(xk[r * 4]);
   }
 #pragma unroll
@@ -258,10 +258,9 @@ __device__ __forceinline__ void act_run(const uint32_t* __restrict__ xk, uint32_
       const int m = m0 + r;
       if (m < 0 || m >= T) { z0 = 0.f; z1 = 0.f; }      // conv zero padding (utils.py:59)
     }
-    const int row = rowS + r;
-    if (row >= vlo && row < vhi) {
+    if ((smask >> r) & 1u) {             // row inside the warp's valid range
       __nv_bfloat162 o = __floats2bfloat162_rn(z0, z1);
-      zk[row * 4] = *reinterpret_cast<uint32_t*>(&o);
+      zk[(rowS + r) * 4] = *reinterpret_cast<uint32_t*>(&o);
     }
   }
 }
@@ -380,6 +379,10 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const TcArgs a) {
       const int ZW = M_TILE + 2 * hc;
       const int vlo = wq * V, vhi = min(vlo + V, ZR);
       const int rowS = vlo - 3 + g * L;
+      uint32_t smask = 0;                 // bit r: local row rowS + r lies in [vlo, vhi)
+#pragma unroll
+      for (int r = 0; r < L; ++r)
+        if (rowS + r >= vlo && rowS + r < vhi) smask |= 1u << r;
       TileCursor cur{prefix};
       int gi = 0;
       for (int w = blockIdx.x; w < total_tiles; w += gridDim.x) {
@@ -404,8 +407,8 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const TcArgs a) {
           if (vlo < ZW) {
             const uint32_t* xk = reinterpret_cast<const uint32_t*>(smem + OFF_X + xb * X_BUF_BYTES) + kg * (XRA * 4) + p;
             uint32_t* zk = reinterpret_cast<uint32_t*>(smem + OFF_Z + zb * Z_BUF_BYTES) + kg * (ZR * 4) + p;
-            if (edge) act_run<L, true>(xk, zk, rowS, vlo, vhi, m0, xlo, T, k, lane);
-            else act_run<L, false>(xk, zk, rowS, vlo, vhi, m0, xlo, T, k, lane);
+            if (edge) act_run<L, true>(xk, zk, rowS, smask, m0, xlo, T, k, lane);
+            else act_run<L, false>(xk, zk, rowS, smask, m0, xlo, T, k, lane);
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // z stores -> async proxy (UMMA)
           __syncwarp();

@@ -116,6 +116,12 @@ struct TcPlan {
   TcLayer rb1[kMaxBlocks][BVG_MAX_DIL], rb2[kMaxBlocks][BVG_MAX_DIL];
   void* lat_blk = nullptr;
   size_t lat_bytes = 0;
+  // the 3 AMP blocks of a stage are independent given xin (models.py:239-244): they run on three
+  // streams (caller's + 2 owned) so their persistent grids back-fill each other's tails
+  void* cbuf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t cbuf_bytes = 0;
+  cudaStream_t aux[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_last[BVG_MAX_KERNELS] = {};
   std::map<std::tuple<const void*, int, int, int>, CUtensorMap> maps;
   std::vector<void*> owned;
 };
@@ -212,12 +218,18 @@ void tc_plan_free(bvg_plan* p) {
   TcPlan* t = static_cast<TcPlan*>(p->tc);
   for (void* q : t->owned) cudaFree(q);
   if (t->lat_blk) cudaFree(t->lat_blk);
+  for (void* q : t->cbuf) if (q) cudaFree(q);
+  for (cudaStream_t q : t->aux) if (q) cudaStreamDestroy(q);
+  if (t->ev_fork) cudaEventDestroy(t->ev_fork);
+  for (cudaEvent_t e : t->ev_last) if (e) cudaEventDestroy(e);
   delete t;
   p->tc = nullptr;
 }
 
 int64_t tc_plan_workspace_bytes(const bvg_plan* p) {
-  return p->tc ? (int64_t) static_cast<TcPlan*>(p->tc)->lat_bytes : 0;
+  if (!p->tc) return 0;
+  const TcPlan* t = static_cast<const TcPlan*>(p->tc);
+  return (int64_t)(t->lat_bytes + 6 * t->cbuf_bytes);
 }
 
 // ------------------------------------------------------------------------------ tensor maps
@@ -382,13 +394,29 @@ int tc_decode(bvg_plan* p, const void* latent, int latent_dtype, const int32_t* 
     if ((rc = launch_tc(p, *map, t->pre, p->conv_pre, nullptr, q, st))) return rc;
   }
   const int nk = p->cfg.num_kernels;
+  // streams / events / per-block buffers for the concurrent AMP blocks
+  const size_t buf_bytes = max_elems * B * sizeof(__nv_bfloat16);
+  if (buf_bytes > t->cbuf_bytes) {
+    BVG_CUDA(cudaDeviceSynchronize());
+    for (void*& qb : t->cbuf) { if (qb) BVG_CUDA(cudaFree(qb)); qb = nullptr; }
+    t->cbuf_bytes = 0;
+    for (void*& qb : t->cbuf) BVG_CUDA(cudaMalloc(&qb, buf_bytes));
+    t->cbuf_bytes = buf_bytes;
+    t->maps.clear();
+  }
+  if (!t->ev_fork) {
+    for (cudaStream_t& q : t->aux) BVG_CUDA(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+    BVG_CUDA(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
+    for (cudaEvent_t& e : t->ev_last) BVG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  // with per-launch profiling on, the blocks are serialised on the caller's stream so that the
+  // CUDA-event duration of a launch is that kernel alone (bvg_plan_set_profiling)
+  const int nstreams = p->profiling ? 1 : std::min(nk, 3);
+  cudaStream_t sj[3] = {st, t->aux[0], t->aux[1]};
+  __nv_bfloat16* xin = bufs[1];
   for (int i = 0; i < p->n_stages; ++i) {
     const int Ci = p->C[i + 1], Ri = p->rate[i + 1], Ti = Tmax * Ri;
-    __nv_bfloat16* free3[3];
-    int nf = 0;
-    for (int qd = 0; qd < 4; ++qd)
-      if (bufs[qd] != cur) free3[nf++] = bufs[qd];
-    __nv_bfloat16 *xin = free3[0], *xr = free3[1], *xt = free3[2], *xs = cur;
+    __nv_bfloat16* xs = cur;            // cur is dead once the ConvTranspose1d has consumed it
     {
       // ConvTranspose1d + cond add (models.py:232-236) as a (k/u)-tap implicit GEMM on the input rate
       const int U = p->cfg.upsample_rates[i], KK = p->ups[i].K, Tin = Tmax * p->rate[i];
@@ -403,9 +431,14 @@ int tc_decode(bvg_plan* p, const void* latent, int latent_dtype, const int32_t* 
       if ((rc = get_map(t, cur, p->C[i], Tin, B, &map))) return rc;
       if ((rc = launch_tc(p, *map, t->ups[i], cw, nullptr, qu, st))) return rc;
     }
+    BVG_CUDA(cudaEventRecord(t->ev_fork, st));
+    for (int js = 1; js < nstreams; ++js) BVG_CUDA(cudaStreamWaitEvent(sj[js], t->ev_fork, 0));
     const int cls = (Ci >= 192) ? 0 : 1;
     for (int j = 0; j < nk; ++j) {
       const int n = i * nk + j;
+      cudaStream_t sq = sj[j % nstreams];
+      __nv_bfloat16* xr = (__nv_bfloat16*)t->cbuf[2 * (j % 3)];
+      __nv_bfloat16* xt = (__nv_bfloat16*)t->cbuf[2 * (j % 3) + 1];
       const __nv_bfloat16* xcur = xin;
       for (int m = 0; m < BVG_MAX_DIL; ++m) {
         const int d = p->cfg.resblock_dilation_sizes[j][m];
@@ -413,7 +446,7 @@ int tc_decode(bvg_plan* p, const void* latent, int latent_dtype, const int32_t* 
         qa.x = xcur; qa.out = xt; qa.dil = d; qa.B = B; qa.Tstride = Ti; qa.rate = Ri; qa.d_len = d_len; qa.cls = cls;
         qa.h_len = h_len; qa.sm_count = p->sm_count;
         if ((rc = get_map(t, xcur, Ci, Ti, B, &map))) return rc;
-        if ((rc = launch_tc(p, *map, t->rb1[n][m], p->rb1[n][m], &p->rba[n][2 * m], qa, st))) return rc;
+        if ((rc = launch_tc(p, *map, t->rb1[n][m], p->rb1[n][m], &p->rba[n][2 * m], qa, sq))) return rc;
 
         const bool last = (m == BVG_MAX_DIL - 1);
         TcLaunch qb;
@@ -422,15 +455,19 @@ int tc_decode(bvg_plan* p, const void* latent, int latent_dtype, const int32_t* 
         if (!last) {
           qb.out = xr;
         } else {
+          // running sum over the blocks (models.py:239-245) is ordered: block j adds onto block j-1
+          if (j > 0) BVG_CUDA(cudaStreamWaitEvent(sq, t->ev_last[j - 1], 0));
           qb.out = xs;
           qb.acc_in = (j > 0) ? xs : nullptr;
           qb.div = (j == nk - 1) ? (float)nk : 1.f;
         }
         if ((rc = get_map(t, xt, Ci, Ti, B, &map))) return rc;
-        if ((rc = launch_tc(p, *map, t->rb2[n][m], p->rb2[n][m], &p->rba[n][2 * m + 1], qb, st))) return rc;
+        if ((rc = launch_tc(p, *map, t->rb2[n][m], p->rb2[n][m], &p->rba[n][2 * m + 1], qb, sq))) return rc;
+        if (last) BVG_CUDA(cudaEventRecord(t->ev_last[j], sq));
         xcur = xr;
       }
     }
+    BVG_CUDA(cudaStreamWaitEvent(st, t->ev_last[nk - 1], 0));    // join
     cur = xs;
   }
   return simt_post_blk(p, cur, wav_out, wav_dtype, B, Tmax, d_len, st);
