@@ -187,6 +187,11 @@ def run_reference(args, rank):
 
 # ----------------------------------------------------------------------------- GPU arm
 def main():
+    # stdout carries exactly ONE JSON line: everything else (NCCL banners, torch warnings, library
+    # prints) is diverted to stderr for the whole run
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

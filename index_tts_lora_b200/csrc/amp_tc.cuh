@@ -101,6 +101,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
       "@P1 bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}\n" ::"r"(bar), "r"(parity) : "memory");
 }
+// Wait that lets the hardware suspend the thread for up to `ns` between polls: used by the roles
+// that are normally far ahead (producers, epilogue) so their polling does not eat issue slots of
+// the activation warps.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t ns) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\tWAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+      "@P1 bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}\n" ::"r"(bar), "r"(parity), "r"(ns) : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
                                             int c3, uint32_t bar) {
   asm volatile(
@@ -384,7 +393,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const TcArgs a) {
       for (int r = 0; r < L; ++r)
         if (rowS + r >= vlo && rowS + r < vhi) smask |= 1u << r;
       TileCursor cur{prefix};
-      int gi = 0;
+      int xb = 0, xph = 0, zb = 0, zph = 0;     // ring slot / phase of the next chunk
       for (int w = blockIdx.x; w < total_tiles; w += gridDim.x) {
         int b, t0, nt;
         cur.locate(w, n_tiles, b, t0, nt);
@@ -394,16 +403,15 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const TcArgs a) {
         // runs whose x window [m0-3, m0+L+2] leaves [0, T) need the replicate clamps (warp-uniform
         // because the run takes part in shuffles)
         const bool edge = __any_sync(0xffffffffu, (m0 - 3 < 0) || (m0 + L + 2 > T - 1));
-        for (int c = 0; c < NCH; ++c, ++gi) {
-          const int xb = gi % NX, xuse = gi / NX, zb = gi & 1, zuse = gi >> 1;
+        for (int c = 0; c < NCH; ++c) {
           const int ch = c * KC + kg * 8 + 2 * p;
           const float2 a2v = __ldg(reinterpret_cast<const float2*>(a.a2 + ch));
           const float2 nhbv = __ldg(reinterpret_cast<const float2*>(a.nhb + ch));
           k.a2 = pk(a2v.x, a2v.y);
           k.nhb = pk(nhbv.x, nhbv.y);
           k.hb = pk(-nhbv.x, -nhbv.y);
-          mbar_wait(BAR_XFULL(xb), xuse & 1);
-          mbar_wait(BAR_ZEMPTY(zb), (zuse & 1) ^ 1);
+          mbar_wait_relaxed(BAR_XFULL(xb), xph, 200);
+          mbar_wait_relaxed(BAR_ZEMPTY(zb), zph ^ 1, 200);
           if (vlo < ZW) {
             const uint32_t* xk = reinterpret_cast<const uint32_t*>(smem + OFF_X + xb * X_BUF_BYTES) + kg * (XRA * 4) + p;
             uint32_t* zk = reinterpret_cast<uint32_t*>(smem + OFF_Z + zb * Z_BUF_BYTES) + kg * (ZR * 4) + p;
@@ -416,6 +424,9 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const TcArgs a) {
             mbar_arrive(BAR_ZFULL(zb));
             mbar_arrive(BAR_XEMPTY(xb));
           }
+          if (++xb == NX) { xb = 0; xph ^= 1; }
+          zb ^= 1;
+          zph ^= (zb == 0);
         }
       }
     }
@@ -431,7 +442,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const TcArgs a) {
           cur.locate(w, n_tiles, b, t0, nt);
           for (int c = 0; c < NCH; ++c, ++gi) {
             const int xb = gi % NX, xuse = gi / NX;
-            mbar_wait(BAR_XEMPTY(xb), (xuse & 1) ^ 1);
+            mbar_wait_relaxed(BAR_XEMPTY(xb), (xuse & 1) ^ 1, 2000);
             mbar_expect_tx(BAR_XFULL(xb), X_TX_BYTES);
             const uint32_t dst = s_base + OFF_X + xb * X_BUF_BYTES;
 #pragma unroll
@@ -454,7 +465,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const TcArgs a) {
             for (int s = 0; s < spc; ++s) {
               const int taps = min(tps, a.K - s * tps);
               const uint32_t bytes = (uint32_t)(taps * tile_bytes);
-              mbar_wait(BAR_WEMPTY(stage), phase ^ 1);
+              mbar_wait_relaxed(BAR_WEMPTY(stage), phase ^ 1, 1000);
               mbar_expect_tx(BAR_WFULL(stage), bytes);
               bulk_load(s_base + OFF_W + stage * W_STAGE_BYTES, src, bytes, BAR_WFULL(stage));
               src += bytes;
@@ -476,20 +487,20 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const TcArgs a) {
         for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++it) {
           const int as = (nacc == 2) ? (it & 1) : 0;
           const int ause = (nacc == 2) ? (it >> 1) : it;
-          mbar_wait(BAR_ACCEMPTY(as), (ause & 1) ^ 1);       // epilogue has drained this accumulator stage
+          mbar_wait_relaxed(BAR_ACCEMPTY(as), (ause & 1) ^ 1, 200);   // epilogue has drained this stage
           tc_fence_after();
           const uint32_t tm = tmem + (uint32_t)(as * 2 * n_tile);
           uint32_t accflag = 0;
           for (int c = 0; c < NCH; ++c, ++gi) {
             const int xb = gi % NX, xuse = gi / NX, zb = gi & 1, zuse = gi >> 1;
-            if (ACT) mbar_wait(BAR_ZFULL(zb), zuse & 1);
-            else mbar_wait(BAR_XFULL(xb), xuse & 1);
+            if (ACT) mbar_wait_relaxed(BAR_ZFULL(zb), zuse & 1, 200);
+            else mbar_wait_relaxed(BAR_XFULL(xb), xuse & 1, 200);
             tc_fence_after();
             const uint32_t aU = (ACT ? (s_base + OFF_Z + zb * Z_BUF_BYTES)
                                      : (s_base + OFF_X + xb * X_BUF_BYTES + (X_LEAD - a.lead) * 16)) >> 4;
             for (int s = 0; s < spc; ++s) {
               const int taps = min(tps, a.K - s * tps);
-              mbar_wait(BAR_WFULL(stage), phase);
+              mbar_wait_relaxed(BAR_WFULL(stage), phase, 200);
               tc_fence_after();
               const uint32_t wU = (s_base + OFF_W + stage * W_STAGE_BYTES) >> 4;
               for (int tj = 0; tj < taps; ++tj) {
@@ -525,115 +536,131 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const TcArgs a) {
       const int as = (nacc == 2) ? (it & 1) : 0;
       const int ause = (nacc == 2) ? (it >> 1) : it;
       float* bs = bias_s + as * 256;
-      asm volatile("bar.sync 1, 128;" ::: "memory");     // previous user of bias_s[as] is done
-      for (int i = etid; i < n_tile; i += 128) {
-        int co = nt * n_tile + i;
-        float v = 0.f;
-        if (co < a.Cout) {
-          if (a.up) co %= a.cphase;
-          v = __ldg(a.bias + co);
-          if (a.bias_b) v += __ldg(a.bias_b + (size_t)b * a.bias_b_stride + co);
-        }
-        bs[i] = v;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if ((a.resid || a.acc_in) && a.up == 0) {
-        // warm L2 with this tile's residual / running-sum rows while its MMAs are still running
-        const int ng = min(n_tile >> 3, cg_total - nt * (n_tile >> 3));
-        for (int mb = 0; mb < 2; ++mb) {
-          const int t = t0 + mb * 128 + q * 32 + lane;
-          if (t >= T) continue;
-          for (int g = 0; g < ng; ++g) {
-            const size_t ii = (((size_t)b * cg_total + nt * (n_tile >> 3) + g) * a.Tstride + t) * 8;
-            if (a.resid) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.resid + ii));
-            if (a.acc_in) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.acc_in + ii));
+      const int cgn0 = nt * (n_tile >> 3);                              // first column group of this tile
+      if (a.bias_b || n_tiles > 1 || it < nacc) {                       // bias row changes with (b, nt) only
+        asm volatile("bar.sync 1, 128;" ::: "memory");                  // previous user of bias_s[as] is done
+        for (int i = etid; i < n_tile; i += 128) {
+          int co = nt * n_tile + i;
+          float v = 0.f;
+          if (co < a.Cout) {
+            if (a.up) co %= a.cphase;
+            v = __ldg(a.bias + co);
+            if (a.bias_b) v += __ldg(a.bias_b + (size_t)b * a.bias_b_stride + co);
           }
+          bs[i] = v;
         }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
-      mbar_wait(BAR_ACCFULL(as), ause & 1);
-      tc_fence_after();
-      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * n_tile);
       const int gpp = a.up ? (a.cphase >> 3) : cg_total;               // channel groups per output row set
       const size_t ubase = (size_t)b * gpp * a.Tstride * 8;            // this utterance's block
       const __nv_bfloat16* resid = a.resid ? a.resid + ubase : nullptr;
       const __nv_bfloat16* accin = a.acc_in ? a.acc_in + ubase : nullptr;
       __nv_bfloat16* outp = a.out + ubase;
+      const int ng = min(n_tile >> 3, cg_total - cgn0);                 // valid column groups
+      const int gstride = a.Tstride * 8;                                // elements between channel groups
+      if ((resid || accin) && a.up == 0) {
+        // warm L2 with this tile's residual / running-sum rows while its MMAs are still running
+#pragma unroll 1
+        for (int mb = 0; mb < 2; ++mb) {
+          const int t = t0 + mb * 128 + q * 32 + lane;
+          if (t >= T) continue;
+          int o = cgn0 * gstride + t * 8;
+#pragma unroll 1
+          for (int g = 0; g < ng; ++g, o += gstride) {
+            if (resid) asm volatile("prefetch.global.L2 [%0];" ::"l"(resid + o));
+            if (accin) asm volatile("prefetch.global.L2 [%0];" ::"l"(accin + o));
+          }
+        }
+      }
+      mbar_wait_relaxed(BAR_ACCFULL(as), ause & 1, 1000);
+      tc_fence_after();
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * n_tile);
+      const float rdiv = 1.0f / a.div;
 #pragma unroll 1
       for (int mb = 0; mb < 2; ++mb) {
         const int t = t0 + mb * 128 + q * 32 + lane;
 #pragma unroll 1
-        for (int cb0 = 0; cb0 < n_tile; cb0 += 32) {
-          const int ngrp = min(4, (n_tile - cb0) >> 3);          // channel groups in this column block
-          // 1) element offset / liveness per group, then the residual / running-sum loads
-          //    off >= 0: live; -1: skip; <= -2: store zeros at -(off+2)
-          int off[4];
-          uint4 rr[4], qq[4];
+        for (int cb0 = 0; cb0 < n_tile; cb0 += 16) {              // 16 accumulator columns = 2 channel groups
+          const int ngrp = min(2, ng - (cb0 >> 3));               // live channel groups in this step
+          if (ngrp <= 0) break;                                    // warp-uniform
+          // element offsets: >= 0 live, -1 skip, <= -2 store zeros at -(off+2)
+          int off[2];
+          uint4 rr[2], qq[2];
+          if (a.up) {                                              // phase scatter of ConvTranspose1d
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            off[kk] = -1;
-            rr[kk] = make_uint4(0, 0, 0, 0);
-            qq[kk] = make_uint4(0, 0, 0, 0);
-            const int cgn = nt * (n_tile >> 3) + (cb0 >> 3) + kk;
-            if (kk >= ngrp || cgn >= cg_total) continue;
-            if (a.up) {                                          // phase scatter of ConvTranspose1d
+            for (int kk = 0; kk < 2; ++kk) {
+              off[kk] = -1;
+              if (kk >= ngrp) continue;
+              const int cgn = cgn0 + (cb0 >> 3) + kk;
               const int r = cgn / gpp, cg = cgn - r * gpp;
               const int to = t * a.up + r - a.pad;
-              if (t >= T || to < 0 || to >= Tin * a.up) continue;
-              off[kk] = (cg * a.Tstride + to) * 8;
-            } else {
-              if (t >= a.Tmax) continue;
-              const int o = (cgn * a.Tstride + t) * 8;
-              off[kk] = (t < T) ? o : -2 - o;
+              if (t < T && to >= 0 && to < Tin * a.up) off[kk] = cg * gstride + to * 8;
             }
-            if (off[kk] >= 0) {
-              if (resid) rr[kk] = *reinterpret_cast<const uint4*>(resid + off[kk]);
-              if (accin) qq[kk] = *reinterpret_cast<const uint4*>(accin + off[kk]);
+          } else {
+            const int o0 = (cgn0 + (cb0 >> 3)) * gstride + t * 8;
+            const int code = (t >= a.Tmax) ? 0 : (t < T ? 1 : 2);
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+              const int o = o0 + kk * gstride;
+              off[kk] = (kk >= ngrp || code == 0) ? -1 : (code == 1 ? o : -2 - o);
             }
           }
-          // 2) accumulators, 16 columns at a time
+          if (resid) {
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            if (hh * 2 >= ngrp) continue;                        // warp-uniform
-            uint32_t v[16];
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                : "r"(taddr + (uint32_t)(mb * n_tile + cb0 + hh * 16)));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            for (int kk = 0; kk < 2; ++kk)
+              if (off[kk] >= 0) rr[kk] = *reinterpret_cast<const uint4*>(resid + off[kk]);
+          }
+          if (accin) {
 #pragma unroll
-            for (int k2 = 0; k2 < 2; ++k2) {
-              const int kk = hh * 2 + k2;
-              const int ox = off[kk];
-              if (ox == -1) continue;
-              uint4 o = make_uint4(0, 0, 0, 0);
-              if (ox >= 0) {
-                float f[8];
+            for (int kk = 0; kk < 2; ++kk)
+              if (off[kk] >= 0) qq[kk] = *reinterpret_cast<const uint4*>(accin + off[kk]);
+          }
+          uint32_t v[16];
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+              : "r"(taddr + (uint32_t)(mb * n_tile + cb0)));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[k2 * 8 + e]) + bs[cb0 + kk * 8 + e];
+          for (int kk = 0; kk < 2; ++kk) {
+            const int ox = off[kk];
+            if (ox == -1) continue;
+            uint4 o = make_uint4(0, 0, 0, 0);
+            if (ox >= 0) {
+              float f[8];
+              const float4 b0 = *reinterpret_cast<const float4*>(bs + cb0 + kk * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(bs + cb0 + kk * 8 + 4);
+              f[0] = __uint_as_float(v[kk * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[kk * 8 + 1]) + b0.y;
+              f[2] = __uint_as_float(v[kk * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[kk * 8 + 3]) + b0.w;
+              f[4] = __uint_as_float(v[kk * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[kk * 8 + 5]) + b1.y;
+              f[6] = __uint_as_float(v[kk * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[kk * 8 + 7]) + b1.w;
+              if (resid) {
                 const uint32_t rw[4] = {rr[kk].x, rr[kk].y, rr[kk].z, rr[kk].w};
-                const uint32_t qw[4] = {qq[kk].x, qq[kk].y, qq[kk].z, qq[kk].w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {        // zero words when there is no residual / running sum
+                for (int e = 0; e < 4; ++e) {
                   f[2 * e] += __uint_as_float(rw[e] << 16);
                   f[2 * e + 1] += __uint_as_float(rw[e] & 0xffff0000u);
                 }
+              }
+              if (accin) {
+                const uint32_t qw[4] = {qq[kk].x, qq[kk].y, qq[kk].z, qq[kk].w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   f[2 * e] += __uint_as_float(qw[e] << 16);
                   f[2 * e + 1] += __uint_as_float(qw[e] & 0xffff0000u);
                 }
-                if (a.div != 1.0f) {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) f[e] = f[e] / a.div;
-                }
-                __nv_bfloat162 p0 = __floats2bfloat162_rn(f[0], f[1]), p1 = __floats2bfloat162_rn(f[2], f[3]);
-                __nv_bfloat162 p2 = __floats2bfloat162_rn(f[4], f[5]), p3 = __floats2bfloat162_rn(f[6], f[7]);
-                o = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
-                               *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
               }
-              *reinterpret_cast<uint4*>(outp + (ox >= 0 ? ox : -(ox + 2))) = o;
+              if (a.div != 1.0f) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] *= rdiv;
+              }
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(f[0], f[1]), p1 = __floats2bfloat162_rn(f[2], f[3]);
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(f[4], f[5]), p3 = __floats2bfloat162_rn(f[6], f[7]);
+              o = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                             *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
             }
+            *reinterpret_cast<uint4*>(outp + (ox >= 0 ? ox : -(ox + 2))) = o;
           }
         }
       }
