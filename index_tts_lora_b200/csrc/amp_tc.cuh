@@ -274,6 +274,31 @@ __device__ __forceinline__ void act_run(const uint32_t* __restrict__ xk, uint32_
   }
 }
 
+__device__ __forceinline__ void load_taps(ActCtx& k, const TcArgs& a) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    k.upE[i] = pk(a.up2[11 - 2 * i], a.up2[11 - 2 * i]);
+    k.upO[i] = pk(a.up2[10 - 2 * i], a.up2[10 - 2 * i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 12; ++i) k.dn[i] = pk(a.dn[i], a.dn[i]);
+}
+
+// Sequence-edge tiles (2 per utterance) take this out-of-line copy so that none of its clamp /
+// select arithmetic is hoisted into the interior path.
+template <int L>
+__device__ __noinline__ void act_run_edge(const uint32_t* xk, uint32_t* zk, int rowS, uint32_t smask, int m0,
+                                          int xlo, int T, u64 a2, u64 nhb, const TcArgs& a, int lane) {
+  ActCtx k;
+  load_taps(k, a);
+  k.a2 = a2;
+  k.nhb = nhb;
+  float h0, h1;
+  upk(nhb, h0, h1);
+  k.hb = pk(-h0, -h1);
+  act_run<L, true>(xk, zk, rowS, smask, m0, xlo, T, k, lane);
+}
+
 // ------------------------------------------------------------------------------ the kernel
 // Persistent: grid = min(#tiles, #SMs); every role walks the same static tile sequence
 // w = blockIdx.x, +gridDim.x, ... (tile = 256 rows x n_tile columns of one utterance; column
@@ -289,8 +314,12 @@ struct TileCursor {            // monotone walk over the per-utterance tile pref
   const int* prefix;
   int b = 0;
   __device__ __forceinline__ void locate(int w, int n_tiles, int& bb, int& t0, int& nt) {
-    const int r = w / n_tiles;
-    nt = w - r * n_tiles;
+    int r = w;
+    nt = 0;
+    if (n_tiles > 1) {               // skip the integer division for single-column-tile layers
+      r = w / n_tiles;
+      nt = w - r * n_tiles;
+    }
     while (r >= prefix[b + 1]) ++b;
     bb = b;
     t0 = (r - prefix[b]) * M_TILE;
@@ -299,7 +328,7 @@ struct TileCursor {            // monotone walk over the per-utterance tile pref
 
 template <int L, bool ACT>
 __global__ void __launch_bounds__(NTHREADS, 1)
-k_amp_tc(const __grid_constant__ CUtensorMap tmx, const TcArgs a) {
+k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tile = a.n_tile, n_tiles = a.n_tiles;
@@ -375,13 +404,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const TcArgs a) {
     reg_inc<96>();
     if (ACT) {
       ActCtx k;
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        k.upE[i] = pk(a.up2[11 - 2 * i], a.up2[11 - 2 * i]);
-        k.upO[i] = pk(a.up2[10 - 2 * i], a.up2[10 - 2 * i]);
-      }
-#pragma unroll
-      for (int i = 0; i < 12; ++i) k.dn[i] = pk(a.dn[i], a.dn[i]);
+      load_taps(k, a);
       // 4 channel groups x 4 warps; a warp's 8 runs of L rows span 8L rows and yield V = 8L-6 z rows
       constexpr int V = 8 * L - 6;
       const int kg = warp & 3, wq = warp >> 2, g = lane >> 2, p = lane & 3;
@@ -415,7 +438,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const TcArgs a) {
           if (vlo < ZW) {
             const uint32_t* xk = reinterpret_cast<const uint32_t*>(smem + OFF_X + xb * X_BUF_BYTES) + kg * (XRA * 4) + p;
             uint32_t* zk = reinterpret_cast<uint32_t*>(smem + OFF_Z + zb * Z_BUF_BYTES) + kg * (ZR * 4) + p;
-            if (edge) act_run<L, true>(xk, zk, rowS, smask, m0, xlo, T, k, lane);
+            if (edge) act_run_edge<L>(xk, zk, rowS, smask, m0, xlo, T, k.a2, k.nhb, a, lane);
             else act_run<L, false>(xk, zk, rowS, smask, m0, xlo, T, k, lane);
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // z stores -> async proxy (UMMA)
@@ -572,7 +595,9 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const TcArgs a) {
           }
         }
       }
-      mbar_wait_relaxed(BAR_ACCFULL(as), ause & 1, 1000);
+      // only one warp polls the accumulator-full mbarrier; the rest sleep on a hardware barrier
+      if (q == 0) mbar_wait_relaxed(BAR_ACCFULL(as), ause & 1, 1000);
+      asm volatile("bar.sync 2, 128;" ::: "memory");
       tc_fence_after();
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * n_tile);
       const float rdiv = 1.0f / a.div;
