@@ -37,8 +37,8 @@ constexpr int X_LEAD = 32;
 constexpr int BOXR = 160;     // TMA box rows (two boxes per channel group)
 constexpr int ZR = 336;       // z rows allocated (16 runs x 21)
 constexpr int NW_ACT = 16;    // warps 0-15 activation | 16 x-TMA | 17 weights | 18 MMA | 19 spare | 20-23 epilogue
-constexpr int NX = 3;         // x ring depth
-constexpr int W_STAGES = 4;
+constexpr int NX_MAX = 3;     // x ring depth (runtime: 2 when the weight ring needs the room)
+constexpr int W_STAGES_MAX = 8;
 constexpr int W_STAGE_BYTES = 16384;
 constexpr int NTHREADS = 768;
 constexpr int MAX_B = 1024;   // utterances per launch (tile-prefix table lives in smem)
@@ -46,15 +46,17 @@ constexpr int MAX_B = 1024;   // utterances per launch (tile-prefix table lives 
 constexpr int X_BUF_BYTES = 4 * XRA * 16;  // 22016
 constexpr int X_TX_BYTES = 4 * XR * 16;    // 20480 bytes actually delivered by TMA
 constexpr int Z_BUF_BYTES = 4 * ZR * 16;   // 21504
-constexpr int OFF_X = 0;
-constexpr int OFF_Z = OFF_X + NX * X_BUF_BYTES;
-constexpr int OFF_W = OFF_Z + 2 * Z_BUF_BYTES;
-constexpr int OFF_BIAS = OFF_W + W_STAGES * W_STAGE_BYTES;
+// shared-memory map: [bias 2x256 f32][tile prefix][barriers][tmem slot] | x ring | z ring | weight ring
+// (ring depths are runtime: nx x-buffers and wst weight stages, chosen per layer by the host)
+constexpr int OFF_BIAS = 0;
 constexpr int OFF_PREFIX = OFF_BIAS + 2 * 256 * 4;
 constexpr int OFF_BAR = OFF_PREFIX + (MAX_B + 8) * 4;
-constexpr int NUM_BARS = 2 * NX + 4 + 2 * W_STAGES + 4;
+constexpr int NUM_BARS = 2 * NX_MAX + 4 + 2 * W_STAGES_MAX + 4;
 constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
-constexpr int SMEM_BYTES = OFF_TMEM + 16;
+constexpr int OFF_X = (OFF_TMEM + 16 + 127) / 128 * 128;
+__host__ __device__ constexpr int off_z(int nx) { return OFF_X + nx * X_BUF_BYTES; }
+__host__ __device__ constexpr int off_w(int nx) { return off_z(nx) + 2 * Z_BUF_BYTES; }
+__host__ __device__ constexpr int smem_bytes(int nx, int wst) { return off_w(nx) + wst * W_STAGE_BYTES; }
 
 struct TcArgs {
   const __nv_bfloat16* wt;     // [ntile][chunk][tap][4][n_tile][8] bf16
@@ -66,6 +68,7 @@ struct TcArgs {
   __nv_bfloat16* out;          // blocked [B][Cout/8][Tstride][8]
   float div;
   int Cin, Cout, K, dil, n_tile, n_tiles, taps_per_stage;
+  int nx, wst;                 // ring depths: x buffers (2..3), weight stages (<= 8)
   int B;
   int Tstride;                 // rows per (b, channel group) in every activation buffer of this stage
   const int* lengths;
@@ -101,14 +104,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
       "@P1 bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}\n" ::"r"(bar), "r"(parity) : "memory");
 }
-// Wait that lets the hardware suspend the thread for up to `ns` between polls: used by the roles
-// that are normally far ahead (producers, epilogue) so their polling does not eat issue slots of
-// the activation warps.
+// Polite wait for the roles that are normally far ahead of the activation warps (producers,
+// epilogue): poll, then sleep `ns` so the polling does not eat the activation warps' issue slots.
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t ns) {
-  asm volatile(
-      "{\n\t.reg .pred P1;\n\tWAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
-      "@P1 bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}\n" ::"r"(bar), "r"(parity), "r"(ns) : "memory");
+  uint32_t done;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    asm volatile("nanosleep.u32 %0;" ::"r"(ns));
+  }
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
                                             int c3, uint32_t bar) {
@@ -162,7 +169,7 @@ __device__ __forceinline__ u64 mul2(u64 a, u64 b) {
   return d;
 }
 __device__ __forceinline__ u64 bf2_to_f2(uint32_t w) {   // two bf16 -> two fp32 (exact)
-  return pk(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+  return pk(__uint_as_float(__byte_perm(w, 0, 0x1044)), __uint_as_float(w & 0xffff0000u));
 }
 
 // ------------------------------------------------------------------------------ activation
@@ -336,14 +343,16 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
 
   const uint32_t s_base = smem_u32(smem);
   const uint32_t bar0 = s_base + OFF_BAR;
+  const int NX = a.nx, W_STAGES = a.wst;
+  const int OFF_Z = off_z(NX), OFF_W = off_w(NX);
   auto BAR_XFULL = [&](int i) { return bar0 + 8 * (0 + i); };
-  auto BAR_XEMPTY = [&](int i) { return bar0 + 8 * (NX + i); };
-  auto BAR_ZFULL = [&](int i) { return bar0 + 8 * (2 * NX + i); };
-  auto BAR_ZEMPTY = [&](int i) { return bar0 + 8 * (2 * NX + 2 + i); };
-  auto BAR_WFULL = [&](int i) { return bar0 + 8 * (2 * NX + 4 + i); };
-  auto BAR_WEMPTY = [&](int i) { return bar0 + 8 * (2 * NX + 4 + W_STAGES + i); };
-  auto BAR_ACCFULL = [&](int i) { return bar0 + 8 * (2 * NX + 4 + 2 * W_STAGES + i); };
-  auto BAR_ACCEMPTY = [&](int i) { return bar0 + 8 * (2 * NX + 6 + 2 * W_STAGES + i); };
+  auto BAR_XEMPTY = [&](int i) { return bar0 + 8 * (NX_MAX + i); };
+  auto BAR_ZFULL = [&](int i) { return bar0 + 8 * (2 * NX_MAX + i); };
+  auto BAR_ZEMPTY = [&](int i) { return bar0 + 8 * (2 * NX_MAX + 2 + i); };
+  auto BAR_WFULL = [&](int i) { return bar0 + 8 * (2 * NX_MAX + 4 + i); };
+  auto BAR_WEMPTY = [&](int i) { return bar0 + 8 * (2 * NX_MAX + 4 + W_STAGES_MAX + i); };
+  auto BAR_ACCFULL = [&](int i) { return bar0 + 8 * (2 * NX_MAX + 4 + 2 * W_STAGES_MAX + i); };
+  auto BAR_ACCEMPTY = [&](int i) { return bar0 + 8 * (2 * NX_MAX + 6 + 2 * W_STAGES_MAX + i); };
   float* bias_s = reinterpret_cast<float*>(smem + OFF_BIAS);
   int* prefix = reinterpret_cast<int*>(smem + OFF_PREFIX);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM);
@@ -377,14 +386,14 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
     if (lane == 0) prefix[0] = 0;
   }
   if (warp == NW_ACT && lane == 0) {
-    for (int i = 0; i < NX; ++i) { mbar_init(BAR_XFULL(i), 1); mbar_init(BAR_XEMPTY(i), ACT ? NW_ACT : 1); }
+    for (int i = 0; i < NX_MAX; ++i) { mbar_init(BAR_XFULL(i), 1); mbar_init(BAR_XEMPTY(i), ACT ? NW_ACT : 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(BAR_ZFULL(i), NW_ACT);
       mbar_init(BAR_ZEMPTY(i), 1);
       mbar_init(BAR_ACCFULL(i), 1);
       mbar_init(BAR_ACCEMPTY(i), 4);
     }
-    for (int i = 0; i < W_STAGES; ++i) { mbar_init(BAR_WFULL(i), 1); mbar_init(BAR_WEMPTY(i), 1); }
+    for (int i = 0; i < W_STAGES_MAX; ++i) { mbar_init(BAR_WFULL(i), 1); mbar_init(BAR_WEMPTY(i), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmx)) : "memory");
   }
@@ -433,13 +442,21 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
           k.a2 = pk(a2v.x, a2v.y);
           k.nhb = pk(nhbv.x, nhbv.y);
           k.hb = pk(-nhbv.x, -nhbv.y);
-          mbar_wait_relaxed(BAR_XFULL(xb), xph, 200);
-          mbar_wait_relaxed(BAR_ZEMPTY(zb), zph ^ 1, 200);
+          mbar_wait(BAR_XFULL(xb), xph);
+          mbar_wait(BAR_ZEMPTY(zb), zph ^ 1);
           if (vlo < ZW) {
             const uint32_t* xk = reinterpret_cast<const uint32_t*>(smem + OFF_X + xb * X_BUF_BYTES) + kg * (XRA * 4) + p;
             uint32_t* zk = reinterpret_cast<uint32_t*>(smem + OFF_Z + zb * Z_BUF_BYTES) + kg * (ZR * 4) + p;
-            if (edge) act_run_edge<L>(xk, zk, rowS, smask, m0, xlo, T, k.a2, k.nhb, a, lane);
-            else act_run<L, false>(xk, zk, rowS, smask, m0, xlo, T, k, lane);
+            if (t0 - hc + vlo >= T) {
+              // the warp's whole row span lies past the end of the utterance: conv zero padding
+#pragma unroll
+              for (int r = 0; r < L; ++r)
+                if ((smask >> r) & 1u) zk[(rowS + r) * 4] = 0u;
+            } else if (edge) {
+              act_run_edge<L>(xk, zk, rowS, smask, m0, xlo, T, k.a2, k.nhb, a, lane);
+            } else {
+              act_run<L, false>(xk, zk, rowS, smask, m0, xlo, T, k, lane);
+            }
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // z stores -> async proxy (UMMA)
           __syncwarp();
@@ -459,13 +476,12 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
       // ===================== x producer (TMA) =====================
       if (lane == 0) {
         TileCursor cur{prefix};
-        int gi = 0;
+        int xb = 0, xph = 0;
         for (int w = blockIdx.x; w < total_tiles; w += gridDim.x) {
           int b, t0, nt;
           cur.locate(w, n_tiles, b, t0, nt);
-          for (int c = 0; c < NCH; ++c, ++gi) {
-            const int xb = gi % NX, xuse = gi / NX;
-            mbar_wait_relaxed(BAR_XEMPTY(xb), (xuse & 1) ^ 1, 2000);
+          for (int c = 0; c < NCH; ++c) {
+            mbar_wait_relaxed(BAR_XEMPTY(xb), xph ^ 1, 500);
             mbar_expect_tx(BAR_XFULL(xb), X_TX_BYTES);
             const uint32_t dst = s_base + OFF_X + xb * X_BUF_BYTES;
 #pragma unroll
@@ -474,6 +490,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
               for (int h = 0; h < 2; ++h)
                 tma_load_4d(dst + kg * (XRA * 16) + h * (BOXR * 16), &tmx, 0, t0 - X_LEAD + h * BOXR, c * 4 + kg, b,
                             BAR_XFULL(xb));
+            if (++xb == NX) { xb = 0; xph ^= 1; }
           }
         }
       }
@@ -488,7 +505,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
             for (int s = 0; s < spc; ++s) {
               const int taps = min(tps, a.K - s * tps);
               const uint32_t bytes = (uint32_t)(taps * tile_bytes);
-              mbar_wait_relaxed(BAR_WEMPTY(stage), phase ^ 1, 1000);
+              mbar_wait_relaxed(BAR_WEMPTY(stage), phase ^ 1, 300);
               mbar_expect_tx(BAR_WFULL(stage), bytes);
               bulk_load(s_base + OFF_W + stage * W_STAGE_BYTES, src, bytes, BAR_WFULL(stage));
               src += bytes;
@@ -506,24 +523,24 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
         // move the 14-bit address field (rows are 16 B apart: +1 unit = +1 time sample)
         const u64 hiA = make_sdesc(0, lboA, 128), hiB = make_sdesc(0, lboB, 128);
         const uint32_t ksA = 2 * lboA / 16, ksB = 2 * lboB / 16, tileU = (uint32_t)tile_bytes / 16;
-        int stage = 0, phase = 0, gi = 0, it = 0;
+        int stage = 0, phase = 0, it = 0;
+        int xb = 0, xph = 0, zb = 0, zph = 0;
         for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++it) {
           const int as = (nacc == 2) ? (it & 1) : 0;
           const int ause = (nacc == 2) ? (it >> 1) : it;
-          mbar_wait_relaxed(BAR_ACCEMPTY(as), (ause & 1) ^ 1, 200);   // epilogue has drained this stage
+          mbar_wait(BAR_ACCEMPTY(as), (ause & 1) ^ 1);        // epilogue has drained this stage
           tc_fence_after();
           const uint32_t tm = tmem + (uint32_t)(as * 2 * n_tile);
           uint32_t accflag = 0;
-          for (int c = 0; c < NCH; ++c, ++gi) {
-            const int xb = gi % NX, xuse = gi / NX, zb = gi & 1, zuse = gi >> 1;
-            if (ACT) mbar_wait_relaxed(BAR_ZFULL(zb), zuse & 1, 200);
-            else mbar_wait_relaxed(BAR_XFULL(xb), xuse & 1, 200);
+          for (int c = 0; c < NCH; ++c) {
+            if (ACT) mbar_wait(BAR_ZFULL(zb), zph);
+            else mbar_wait(BAR_XFULL(xb), xph);
             tc_fence_after();
             const uint32_t aU = (ACT ? (s_base + OFF_Z + zb * Z_BUF_BYTES)
                                      : (s_base + OFF_X + xb * X_BUF_BYTES + (X_LEAD - a.lead) * 16)) >> 4;
             for (int s = 0; s < spc; ++s) {
               const int taps = min(tps, a.K - s * tps);
-              mbar_wait_relaxed(BAR_WFULL(stage), phase, 200);
+              mbar_wait(BAR_WFULL(stage), phase);
               tc_fence_after();
               const uint32_t wU = (s_base + OFF_W + stage * W_STAGE_BYTES) >> 4;
               for (int tj = 0; tj < taps; ++tj) {
@@ -539,6 +556,9 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
               if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
             }
             umma_commit(ACT ? BAR_ZEMPTY(zb) : BAR_XEMPTY(xb));
+            if (++xb == NX) { xb = 0; xph ^= 1; }
+            zb ^= 1;
+            zph ^= (zb == 0);
           }
           umma_commit(BAR_ACCFULL(as));
         }
@@ -596,7 +616,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
         }
       }
       // only one warp polls the accumulator-full mbarrier; the rest sleep on a hardware barrier
-      if (q == 0) mbar_wait_relaxed(BAR_ACCFULL(as), ause & 1, 1000);
+      if (q == 0) mbar_wait_relaxed(BAR_ACCFULL(as), ause & 1, 300);
       asm volatile("bar.sync 2, 128;" ::: "memory");
       tc_fence_after();
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * n_tile);

@@ -50,14 +50,14 @@ static void conv_cost(const Ctx& c, const ConvArgs& a, int K, double* flops, dou
            (double)a.Cin * a.Cout * K * c.elt;
 }
 
-template <int K, bool ACT, int TY, int NC, int NT, int XL>
+template <int K, bool ACT, int TY, int NC, int NT, int XL, bool FAST = false>
 static int launch_conv(const ConvArgs& a, int B, const Ctx& c) {
   cudaStream_t st = c.st;
   constexpr int TX = 256 / TY, TT = TX * NT, COB = TY * NC, CK = 8;
   const int hc = a.dil * (K - 1) / 2;
   const int ZW = TT + 2 * hc, SW = 2 * ZW + 12, XW = ZW + 12;
   const size_t smem = sizeof(float) * (size_t)(CK * ZW + CK * K * COB + (ACT ? CK * (SW + XW) : 0));
-  auto kern = k_conv_f32<K, ACT, TY, NC, NT, XL>;
+  auto kern = k_conv_f32<K, ACT, TY, NC, NT, XL, FAST>;
   static bool attr_set = false;   // per template instance
   if (!attr_set) {
     BVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -377,7 +377,7 @@ int simt_post_blk(bvg_plan* p, const void* x_blk, void* wav, int wav_dtype, int 
   a.lengths = d_len; a.rate = p->rate[S]; a.Tmax = Tmax * p->rate[S];
   a.tanh_out = 1; a.zero_tail = 1;
   fill_act(a.act, p->act_post);
-  return launch_conv<7, true, 1, 1, 2, 2>(a, B, cx);
+  return launch_conv<7, true, 1, 1, 2, 2, true>(a, B, cx);
 }
 
 void tc_pack_conv_w(const float* w, float* wp, int Cout, int Cin, int K, cudaStream_t st) {

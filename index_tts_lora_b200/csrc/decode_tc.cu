@@ -303,10 +303,12 @@ static int launch_inst(const CUtensorMap& map, const TcArgs& a, dim3 grid, cudaS
   auto kern = k_amp_tc<L, ACT>;
   static bool attr = false;
   if (!attr) {
-    BVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    BVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
-  kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(map, a);
+  const int smem = smem_bytes(a.nx, a.wst);
+  if (smem > 227 * 1024) return fail(BVG_ERR_STATE, "k_amp_tc smem plan %d B exceeds 227 KB", smem);
+  kern<<<grid, NTHREADS, smem, st>>>(map, a);
   BVG_CUDA(cudaGetLastError());
   return 0;
 }
@@ -318,6 +320,10 @@ static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, cons
   a.resid = q.resid; a.acc_in = q.acc_in; a.out = q.out; a.div = q.div;
   a.Cin = cw.Cin; a.Cout = cw.Cout; a.K = cw.K; a.dil = q.dil;
   a.n_tile = L.n_tile; a.n_tiles = L.n_tiles; a.taps_per_stage = L.tps; a.B = q.B;
+  // ring depths: layers that stream big weight tiles (16 KB per tap) are bound by the L2 latency of
+  // the weight ring, so they trade the third x buffer for 8 weight stages; narrow layers keep 3 x buffers
+  const int stage_bytes = L.tps * L.n_tile * 64;
+  if (stage_bytes * 4 > 32 * 1024) { a.nx = 2; a.wst = 8; } else { a.nx = 3; a.wst = 4; }
   a.Tstride = q.out_tstride ? q.out_tstride : q.Tstride;
   a.lengths = q.d_len; a.rate = q.rate; a.Tmax = q.Tstride;
   a.up = q.up; a.pad = q.pad; a.cphase = q.cphase;

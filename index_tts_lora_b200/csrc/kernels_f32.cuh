@@ -17,6 +17,13 @@ namespace bvg {
 //   z[m]    = sum_k dn[k] * s[clamp(2m+k-5, 0, 2T-1)]           filter.py:87-96
 // `xw` must hold x[clamp(j)] for j = xlo .. ; n is already clamped to [0, 2T).
 // ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float __tanhf_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));   // MUFU.TANH, abs err ~5e-4 (bf16 path only)
+  return y;
+}
+
+template <bool FAST = false>
 __device__ __forceinline__ float snake_up_sample(const float* __restrict__ xw, int xlo, int n,
                                                  const ActParams& ap, float a, float invb) {
   const int m = n >> 1;
@@ -31,7 +38,7 @@ __device__ __forceinline__ float snake_up_sample(const float* __restrict__ xw, i
     for (int i = 0; i < 6; ++i) y = fmaf(ap.up[10 - 2 * i], p[i], y);
   }
   y *= 2.0f;
-  const float sn = sinf(y * a);
+  const float sn = FAST ? __sinf(y * a) : sinf(y * a);   // FAST: MUFU.SIN (bf16 path only)
   return y + invb * (sn * sn);
 }
 
@@ -65,7 +72,7 @@ struct ConvArgs {
 
 // XL: layout of x — 0 channel-major fp32 [B][Cin][T]; 1 time-major latent [B][Tmax][Cin] (any
 // dtype); 2 blocked bf16 [B][Cin/8][T][8] (the tcgen05 path's layout, used by conv_post there).
-template <int K, bool ACT, int TY, int NC, int NT, int XL>
+template <int K, bool ACT, int TY, int NC, int NT, int XL, bool FAST = false>
 __global__ void __launch_bounds__(256) k_conv_f32(const ConvArgs a) {
   constexpr bool TM_IN = (XL == 1);
   constexpr int TX = 256 / TY;
@@ -135,8 +142,8 @@ __global__ void __launch_bounds__(256) k_conv_f32(const ConvArgs a) {
         const int c = idx / SW, i = idx % SW;
         int n = n_lo + i;
         n = n < 0 ? 0 : (n > 2 * T - 1 ? 2 * T - 1 : n);
-        ss[idx] = snake_up_sample(xs + c * XW, x_lo, n, a.act, __ldg(a.act.a + ci0 + c),
-                                  __ldg(a.act.invb + ci0 + c));
+        ss[idx] = snake_up_sample<FAST>(xs + c * XW, x_lo, n, a.act, __ldg(a.act.a + ci0 + c),
+                                        __ldg(a.act.invb + ci0 + c));
       }
       __syncthreads();
       // ---- z = downsample(s); conv zero padding outside [0,T) (utils.py:59)
@@ -209,7 +216,7 @@ __global__ void __launch_bounds__(256) k_conv_f32(const ConvArgs a) {
       if (a.resid) v = v + __ldg(a.resid + o);
       if (a.acc_in) v = a.acc_in[o] + v;
       if (a.div != 1.0f) v = v / a.div;
-      if (a.tanh_out) v = tanhf(v);
+      if (a.tanh_out) v = FAST ? __tanhf_fast(v) : tanhf(v);
       st_dyn(a.out, o, a.out_dtype, v);
     }
   }
