@@ -10,6 +10,8 @@ A "step" is one pass of the hot path — `wav, _ = bigvgan(latent, mel_ref)` (in
               configuration the throughput / roofline metric is quoted on]
     utt6p7s   1 utterance x 157 frames (6.70 s)                          [configs[1], latency case]
     mixed256  256 utterances, 47..469 frames, sharded by utterance over the ranks (LPT)  [configs[3]]
+    long60s   ONE 1406-frame (59.99 s) utterance split along time over the ranks; every rank decodes
+              its frame range plus receptive-field halos (overlap-recompute, bvg_decode_shard) [configs[4]]
 Multi-GPU: utterances are independent, so ranks share nothing — no data-path collective; NCCL is
 used only for the barrier and the max-over-ranks of the device time.  `scaling` is "weak" for
 b16x10s / utt6p7s (every rank decodes its own batch) and "strong" for mixed256.
@@ -57,6 +59,8 @@ def workload_lengths(name: str, rank: int, world: int):
         return [234] * 16, 16 * 234 * world, "weak"
     if name == "utt6p7s":
         return [157], 157 * world, "weak"
+    if name == "long60s":
+        return [1406], 1406, "strong"
     if name == "mixed256":
         lens = synth.synth_lengths(256, 47, 469, seed=2)
         shards = lpt_assign(lens, world)
@@ -164,7 +168,7 @@ def run_reference(args, rank):
     import torch
 
     threads = os.cpu_count() or 1
-    frames = {"b16x10s": 234, "utt6p7s": 157, "mixed256": 234}[args.workload]
+    frames = {"b16x10s": 234, "utt6p7s": 157, "mixed256": 234, "long60s": 234}[args.workload]
     steps = max(1, args.steps)
     warm = max(0, min(args.warmup, 1))
     times = cpu_oracle_run(frames, warm + steps, threads)[warm:]
@@ -198,7 +202,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--workload", default="b16x10s", choices=["b16x10s", "utt6p7s", "mixed256"])
+    ap.add_argument("--workload", default="b16x10s", choices=["b16x10s", "utt6p7s", "mixed256", "long60s"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-l2-flush", action="store_true")
     args = ap.parse_args()
@@ -260,7 +264,35 @@ def main():
     flush_buf = None if args.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
 
+    shard = None
+    if args.workload == "long60s":
+        from index_tts_lora_b200.sharding import time_shards
+        rf = lib.bvg_receptive_field_frames(plan)
+        fb, fe, hl, hr = time_shards(1406, world, rf)[rank]
+        full = synth.synth_latent(1, 1406, h.gpt_dim, seed=0).to(lat_dtype)       # same utterance on every rank
+        sh_dev = full[0, fb - hl: fe + hr].contiguous().to(dev)
+        sh_host = full[0, fb - hl: fe + hr].contiguous().pin_memory()
+        sh_out = torch.empty((fe - fb) * UP, dtype=torch.int16, device=dev)
+        sh_out_host = torch.empty((fe - fb) * UP, dtype=torch.int16).pin_memory()
+        shard = (fb, fe, hl, hr)
+        my_frames = fe - fb
+
+    def step_shard(host: bool):
+        fb, fe, hl, hr = shard
+        emb = m.speaker_embedding(mel).reshape(1, -1).float().contiguous()
+        src = sh_dev
+        if host:
+            src = sh_host.to(dev, non_blocking=True)
+        _lib.check(lib.bvg_decode_shard(plan, src.data_ptr(), _lib.torch_dtype_code(lat_dtype), fb, fe, 1406, hl, hr,
+                                        emb.data_ptr(), sh_out.data_ptr(), _lib.BVG_I16, prec, stream.cuda_stream),
+                   "bvg_decode_shard")
+        if host:
+            sh_out_host.copy_(sh_out, non_blocking=True)
+            stream.synchronize()
+
     def step_device():
+        if shard is not None:
+            return step_shard(False)
         out = None
         for bi, bl in enumerate(batches):
             emb = m.speaker_embedding(mel)                      # ECAPA, part of forward (models.py:204)
@@ -268,6 +300,8 @@ def main():
         return out
 
     def step_host():
+        if shard is not None:
+            return step_shard(True)
         for bi, bl in enumerate(batches):
             emb = m.speaker_embedding(mel).reshape(1, -1).float().expand(len(bl), -1).contiguous()
             _lib.check(lib.bvg_decode_host(plan, host_lat[bi].data_ptr(), _lib.torch_dtype_code(lat_dtype),
@@ -349,6 +383,16 @@ def main():
                     "how": "per-launch CUDA events on the launching stream over a second pass of K steps with "
                            "the three AMP blocks of a stage serialised (they overlap on 3 streams in the timed pass)",
                     "serialised_ms_per_step": ms_prof / K}
+        # DRAM traffic of the same kernel class from the committed ncu capture (b16x10s only):
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the 108 AMP launches
+        tpath = os.path.join(ROOT, "profiles", "r01_amp_traffic_b16x10s.json")
+        if args.workload == "b16x10s" and args.precision == "bf16" and os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            roofline["traffic"] = tj["amp_dram_bytes_per_launch"]
+            roofline["traffic_source"] = "profiles/r01_launches_v5_b16x10s_time_dram.csv (ncu, per launch avg)"
+            roofline["algorithmic_bytes_per_launch"] = tj["amp_alg_bytes_per_launch"]
+            roofline["algorithmic_flops_per_launch"] = tj["amp_flops_per_launch"]
         by_class = {}
         for i, nm in enumerate(["amp_tensor_stages", "amp_small_stages", "pre_ups_cond", "post"]):
             if cls_n[i]:
@@ -358,6 +402,8 @@ def main():
                                 "hbm_frac": cls_by[i] / (cls_ms[i] * 1e-3) / 1e9 / peaks["hbm_gbs"] if cls_ms[i] else 0.0}
         h2d = sum(x.numel() * x.element_size() for x in host_lat)
         d2h = sum(x.numel() * x.element_size() for x in host_wav)
+        if shard is not None:
+            h2d, d2h = sh_host.numel() * sh_host.element_size(), sh_out_host.numel() * 2
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
@@ -367,7 +413,9 @@ def main():
                        "audio_seconds_per_step": audio_s_total, "weights": "random-init (synth profile 'init', seed 1234)",
                        "l2": ("working set >> 126 MB L2 per step" +
                               ("" if args.no_l2_flush else " + 256 MiB L2 flush between steps (outside the events)")),
-                       "parallelism": f"utterance-sharded x{world}, no data-path collective"},
+                       "parallelism": (f"time-split x{world} with {shard[2]}/{shard[3]}-frame halos on rank 0 "
+                                       "(overlap-recompute, no exchange)" if shard is not None else
+                                       f"utterance-sharded x{world}, no data-path collective")},
             "gpu_launches": launches * K,
             "tensor_frac_of_step": (FLOP_PER_FRAME * my_frames / (ms_dev / K * 1e-3) / 1e12) / peak_tf,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
