@@ -265,7 +265,18 @@ def main():
     stream = torch.cuda.current_stream(dev)
 
     shard = None
-    if args.workload == "long60s":
+    p2p = None
+    if args.workload == "long60s" and world > 1:
+        # per-stage NVLink P2P halo exchange (CUDA-IPC peer stores + flags); torch.distributed only swaps
+        # the IPC handles once and provides the host barrier between decodes
+        from index_tts_lora_b200.longform import TimeSplitP2P
+        full = synth.synth_latent(1, 1406, h.gpt_dim, seed=0).to(lat_dtype)
+        p2p = TimeSplitP2P(m, 1406, rank, world).setup(dev).connect_distributed()
+        p2p_win_host = p2p.window(full).pin_memory()
+        p2p_win = p2p_win_host.to(dev)
+        p2p_out_host = torch.empty((p2p.fe - p2p.fb) * UP, dtype=torch.int16).pin_memory()
+        my_frames = p2p.fe - p2p.fb
+    elif args.workload == "long60s":
         from index_tts_lora_b200.sharding import time_shards
         rf = lib.bvg_receptive_field_frames(plan)
         fb, fe, hl, hr = time_shards(1406, world, rf)[rank]
@@ -290,7 +301,18 @@ def main():
             sh_out_host.copy_(sh_out, non_blocking=True)
             stream.synchronize()
 
+    def step_p2p(host: bool):
+        dist.barrier()                                   # no rank may start decode n+1 while a neighbour is in n
+        emb = m.speaker_embedding(mel)
+        win = p2p_win_host.to(dev, non_blocking=True) if host else p2p_win
+        out = p2p.decode(win, emb, out_dtype=torch.int16)
+        if host:
+            p2p_out_host.copy_(out, non_blocking=True)
+            stream.synchronize()
+
     def step_device():
+        if p2p is not None:
+            return step_p2p(False)
         if shard is not None:
             return step_shard(False)
         out = None
@@ -300,6 +322,8 @@ def main():
         return out
 
     def step_host():
+        if p2p is not None:
+            return step_p2p(True)
         if shard is not None:
             return step_shard(True)
         for bi, bl in enumerate(batches):
@@ -404,6 +428,8 @@ def main():
         d2h = sum(x.numel() * x.element_size() for x in host_wav)
         if shard is not None:
             h2d, d2h = sh_host.numel() * sh_host.element_size(), sh_out_host.numel() * 2
+        if p2p is not None:
+            h2d, d2h = p2p_win_host.numel() * p2p_win_host.element_size(), p2p_out_host.numel() * 2
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
@@ -413,7 +439,9 @@ def main():
                        "audio_seconds_per_step": audio_s_total, "weights": "random-init (synth profile 'init', seed 1234)",
                        "l2": ("working set >> 126 MB L2 per step" +
                               ("" if args.no_l2_flush else " + 256 MiB L2 flush between steps (outside the events)")),
-                       "parallelism": (f"time-split x{world} with {shard[2]}/{shard[3]}-frame halos on rank 0 "
+                       "parallelism": (f"time-split x{world}, per-stage NVLink P2P halo exchange (CUDA-IPC peer stores + "
+                                       "flags, 6 exchanges per decode, no NCCL on the data path)" if p2p is not None else
+                                       f"time-split x{world} with {shard[2]}/{shard[3]}-frame halos on rank 0 "
                                        "(overlap-recompute, no exchange)" if shard is not None else
                                        f"utterance-sharded x{world}, no data-path collective")},
             "gpu_launches": launches * K,

@@ -132,6 +132,37 @@ int bvg_decode_shard(bvg_plan* plan, const void* latent, int latent_dtype, int f
                      int f_end, int f_total, int halo_l, int halo_r, const float* spk_emb,
                      void* wav_out, int wav_dtype, int precision, void* stream);
 
+/* ---- time split with NVLink P2P halo exchange (one process per GPU; bf16 path) --------------
+ * A long utterance is cut into contiguous frame ranges, one per GPU.  Every rank calls
+ * bvg_shard_setup with its range and its neighbours' sizes, exports three CUDA-IPC handles
+ * (bvg_shard_export) that the host exchanges by any means (torch.distributed object gather),
+ * connects to its neighbours (bvg_shard_connect) and then runs the S+1 phases of bvg_shard_run
+ * in order.  Between phases the ranks exchange receptive-field halos of the stage output by
+ * direct peer stores over NVLink plus a system-scope flag per (side, stage); `wait` != 0 makes a
+ * phase first wait (on the device) for its neighbours' flags of this `epoch` (use a new, larger
+ * epoch for every decode and put a host barrier between decodes).  With all "ranks" in ONE
+ * process on one device (tests) connect by pointer and run phase p of every rank before phase
+ * p+1 of any, with wait = 0. */
+typedef struct bvg_shard_geom {
+  int32_t f_begin, f_end, f_total; /* this rank decodes latent frames [f_begin, f_end) of f_total */
+  int32_t own_left, own_right;     /* frame counts of the left / right neighbour (0 if none) */
+  int32_t own_max;                 /* largest frame count over all ranks (common buffer stride) */
+} bvg_shard_geom;
+int bvg_shard_setup(bvg_plan* plan, const bvg_shard_geom* geom, void* stream);
+/* latent frames of context the caller must supply on every side that is not a sequence end */
+int bvg_shard_halo_frames(bvg_plan* plan);
+int bvg_shard_export(bvg_plan* plan, uint8_t* handles /* 3 x 64 bytes */);
+int bvg_shard_connect(bvg_plan* plan, int side /* 0 left, 1 right */, const uint8_t* handles);
+int bvg_shard_local_ptrs(bvg_plan* plan, void** ws0, void** ws1, void** flags);
+int bvg_shard_connect_ptr(bvg_plan* plan, int side, void* ws0, void* ws1, void* flags);
+/* phase 0 needs `latent` = frames [f_begin - halo_l, f_end + halo_r) (halo = bvg_shard_halo_frames
+ * on non-end sides) and spk_emb [1, D]; the last phase (num_upsamples) writes the rank's own
+ * (f_end - f_begin) * prod(upsample_rates) samples to wav_out. */
+int bvg_shard_run(bvg_plan* plan, int phase, const void* latent, int latent_dtype, const float* spk_emb,
+                  void* wav_out, int wav_dtype, int epoch, int wait, void* stream);
+/* 0 = fine, 1/2 = timed out waiting for the left/right neighbour (synchronises the device) */
+int bvg_shard_error(bvg_plan* plan);
+
 /* Number of latent frames of context each side that makes bvg_decode_shard exact
  * (receptive field of the generator in latent frames, rounded up). */
 int bvg_receptive_field_frames(const bvg_plan* plan);

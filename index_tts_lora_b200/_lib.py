@@ -50,6 +50,11 @@ class BvgProfile(C.Structure):
                 ("bytes", C.c_double * PROFILE_CLASSES), ("launches", C.c_int32 * PROFILE_CLASSES)]
 
 
+class BvgShardGeom(C.Structure):
+    _fields_ = [("f_begin", C.c_int32), ("f_end", C.c_int32), ("f_total", C.c_int32),
+                ("own_left", C.c_int32), ("own_right", C.c_int32), ("own_max", C.c_int32)]
+
+
 # every symbol include/bvg.h declares: name -> (restype, argtypes)
 _P, _I, _L = C.c_void_p, C.c_int, C.c_int64
 SYMBOLS = {
@@ -62,6 +67,14 @@ SYMBOLS = {
     "bvg_decode_host": (_I, [_P, _P, _I, C.POINTER(C.c_int32), _I, _I, _P, _P, _I, _I, _P]),
     "bvg_decode_shard": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P]),
     "bvg_receptive_field_frames": (_I, [_P]),
+    "bvg_shard_setup": (_I, [_P, C.POINTER(BvgShardGeom), _P]),
+    "bvg_shard_halo_frames": (_I, [_P]),
+    "bvg_shard_export": (_I, [_P, _P]),
+    "bvg_shard_connect": (_I, [_P, _I, _P]),
+    "bvg_shard_local_ptrs": (_I, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
+    "bvg_shard_connect_ptr": (_I, [_P, _I, _P, _P, _P]),
+    "bvg_shard_run": (_I, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _P]),
+    "bvg_shard_error": (_I, [_P]),
     "bvg_plan_workspace_bytes": (_L, [_P]),
     "bvg_plan_last_launches": (_I, [_P]),
     "bvg_plan_set_profiling": (_I, [_P, _I]),

@@ -69,6 +69,8 @@ struct TcArgs {
   float div;
   int Cin, Cout, K, dil, n_tile, n_tiles, taps_per_stage;
   int nx, wst;                 // ring depths: x buffers (2..3), weight stages (<= 8)
+  int st_lo, st_hi;            // conv mode: only rows in [st_lo, st_hi) are stored (time-split shards keep
+                               // their hands off the halo rows that the neighbouring GPUs write)
   int B;
   int Tstride;                 // rows per (b, channel group) in every activation buffer of this stage
   const int* lengths;
@@ -643,7 +645,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
             }
           } else {
             const int o0 = (cgn0 + (cb0 >> 3)) * gstride + t * 8;
-            const int code = (t >= a.Tmax) ? 0 : (t < T ? 1 : 2);
+            const int code = (t >= a.Tmax || t < a.st_lo || t >= a.st_hi) ? 0 : (t < T ? 1 : 2);
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) {
               const int o = o0 + kk * gstride;
@@ -715,7 +717,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
       if (lane == 0) mbar_arrive(BAR_ACCEMPTY(as));
       // un-activated consumers (ConvTranspose1d) read one row past the end: keep rows [T, T+8) zero
       // when the utterance ends exactly on this tile's boundary (otherwise they were zeroed above)
-      if (a.up == 0 && T == t0 + M_TILE && T < a.Tmax && q == 0) {
+      if (a.up == 0 && T == t0 + M_TILE && T < a.Tmax && T < a.st_hi && q == 0) {
         const int ngr = min(n_tile >> 3, cg_total - nt * (n_tile >> 3));
         for (int i = lane; i < ngr * 8; i += 32) {
           const int g = i >> 3, r = T + (i & 7);

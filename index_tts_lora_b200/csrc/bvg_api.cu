@@ -629,6 +629,40 @@ int bvg_decode_shard(bvg_plan* p, const void* latent, int latent_dtype, int f_be
   return 0;
 }
 
+int bvg_shard_setup(bvg_plan* p, const bvg_shard_geom* g, void* stream) {
+  BVG_REQUIRE(p && g, "bvg_shard_setup: null argument");
+  if (!p->weights_loaded) return fail(BVG_ERR_STATE, "bvg_shard_setup: no weights loaded");
+  BVG_CUDA(cudaSetDevice(p->device));
+  return tc_shard_setup(p, g, (cudaStream_t)stream);
+}
+int bvg_shard_halo_frames(bvg_plan* p) { return p ? tc_shard_halo_frames(p) : -1; }
+int bvg_shard_export(bvg_plan* p, uint8_t* handles) {
+  BVG_REQUIRE(p && handles, "bvg_shard_export: null argument");
+  BVG_CUDA(cudaSetDevice(p->device));
+  return tc_shard_export(p, handles);
+}
+int bvg_shard_connect(bvg_plan* p, int side, const uint8_t* handles) {
+  BVG_REQUIRE(p && handles, "bvg_shard_connect: null argument");
+  BVG_CUDA(cudaSetDevice(p->device));
+  return tc_shard_connect(p, side, handles, nullptr, nullptr, nullptr);
+}
+int bvg_shard_local_ptrs(bvg_plan* p, void** ws0, void** ws1, void** flags) {
+  BVG_REQUIRE(p && ws0 && ws1 && flags, "bvg_shard_local_ptrs: null argument");
+  return tc_shard_local_ptrs(p, ws0, ws1, flags);
+}
+int bvg_shard_connect_ptr(bvg_plan* p, int side, void* ws0, void* ws1, void* flags) {
+  BVG_REQUIRE(p && ws0 && ws1 && flags, "bvg_shard_connect_ptr: null argument");
+  return tc_shard_connect(p, side, nullptr, ws0, ws1, flags);
+}
+int bvg_shard_run(bvg_plan* p, int phase, const void* latent, int latent_dtype, const float* spk_emb, void* wav_out,
+                  int wav_dtype, int epoch, int wait, void* stream) {
+  BVG_REQUIRE(p, "bvg_shard_run: null plan");
+  BVG_REQUIRE(wav_dtype >= BVG_F32 && wav_dtype <= BVG_I16, "bvg_shard_run: bad wav dtype");
+  BVG_CUDA(cudaSetDevice(p->device));
+  return tc_shard_run(p, phase, latent, latent_dtype, spk_emb, wav_out, wav_dtype, epoch, wait, (cudaStream_t)stream);
+}
+int bvg_shard_error(bvg_plan* p) { return p ? tc_shard_error(p) : -1; }
+
 int64_t bvg_plan_workspace_bytes(const bvg_plan* p) {
   return p ? (int64_t)(4 * p->ws_bytes + tc_plan_workspace_bytes(p)) : -1;
 }

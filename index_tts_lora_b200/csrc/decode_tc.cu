@@ -2,6 +2,8 @@
 // launch selection and the decode orchestration (models.py:212-252) on the blocked bf16 layout.
 #include <cuda.h>
 
+#include <string.h>
+
 #include <map>
 #include <tuple>
 #include <vector>
@@ -121,8 +123,9 @@ struct TcPlan {
   void* cbuf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t cbuf_bytes = 0;
   cudaStream_t aux[2] = {nullptr, nullptr};
+  void* shard = nullptr;            // ShardState (time-split P2P decode)
   cudaEvent_t ev_fork = nullptr, ev_last[BVG_MAX_KERNELS] = {};
-  std::map<std::tuple<const void*, int, int, int>, CUtensorMap> maps;
+  std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> maps;
   std::vector<void*> owned;
 };
 
@@ -213,9 +216,12 @@ int tc_plan_pack(bvg_plan* p, cudaStream_t st) {
   return 0;
 }
 
+void tc_shard_free(TcPlan* t);
+
 void tc_plan_free(bvg_plan* p) {
   if (!p->tc) return;
   TcPlan* t = static_cast<TcPlan*>(p->tc);
+  tc_shard_free(t);
   for (void* q : t->owned) cudaFree(q);
   if (t->lat_blk) cudaFree(t->lat_blk);
   for (void* q : t->cbuf) if (q) cudaFree(q);
@@ -251,10 +257,12 @@ static PFN_encodeTiled get_encode() {
 
 // blocked bf16 activation buffer [B][C/8][Tstride][8] as a 4-D tensor {8, Tstride, C/8, B};
 // box {8, BOXR, 1, 1}; out-of-range rows / channel groups read as zero.
-static int make_map(const void* base, int C, int Tstride, int B, CUtensorMap* out) {
+static int make_map(const void* base, int C, int Tstride, int B, CUtensorMap* out, int rows = 0) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return fail(BVG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t dims[4] = {8, (cuuint64_t)Tstride, (cuuint64_t)(C / 8), (cuuint64_t)B};
+  // `rows` < Tstride when `base` points into the middle of a buffer (time-split windows): rows past
+  // the end of the allocation are then out of bounds for the TMA unit (zero-filled, never fetched)
+  cuuint64_t dims[4] = {8, (cuuint64_t)(rows > 0 ? rows : Tstride), (cuuint64_t)(C / 8), (cuuint64_t)B};
   cuuint64_t strides[3] = {16, (cuuint64_t)Tstride * 16, (cuuint64_t)(C / 8) * Tstride * 16};
   cuuint32_t box[4] = {8, (cuuint32_t)BOXR, 1, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
@@ -265,13 +273,13 @@ static int make_map(const void* base, int C, int Tstride, int B, CUtensorMap* ou
   return 0;
 }
 
-static int get_map(TcPlan* t, const void* base, int C, int Tstride, int B, const CUtensorMap** out) {
-  auto key = std::make_tuple(base, C, Tstride, B);
+static int get_map(TcPlan* t, const void* base, int C, int Tstride, int B, const CUtensorMap** out, int rows = 0) {
+  auto key = std::make_tuple(base, C, Tstride, B, rows);
   auto it = t->maps.find(key);
   if (it == t->maps.end()) {
     if (t->maps.size() > 4096) t->maps.clear();
     CUtensorMap m;
-    int rc = make_map(base, C, Tstride, B, &m);
+    int rc = make_map(base, C, Tstride, B, &m, rows);
     if (rc) return rc;
     it = t->maps.emplace(key, m).first;
   }
@@ -296,6 +304,7 @@ struct TcLaunch {
   int sm_count = 0;
   int up = 0, pad = 0, cphase = 0;   // ConvTranspose1d mode
   int out_tstride = 0;               // defaults to Tstride
+  int st_lo = 0, st_hi = 0x7fffffff; // store range (rows) of a conv-mode launch
 };
 
 template <int L, bool ACT>
@@ -327,6 +336,7 @@ static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, cons
   a.Tstride = q.out_tstride ? q.out_tstride : q.Tstride;
   a.lengths = q.d_len; a.rate = q.rate; a.Tmax = q.Tstride;
   a.up = q.up; a.pad = q.pad; a.cphase = q.cphase;
+  a.st_lo = q.st_lo; a.st_hi = q.st_hi;
   const int hc = q.dil * (cw.K - 1) / 2;
   a.lead = q.up ? cw.K - 1 : hc;
   if (aw) {
@@ -358,16 +368,29 @@ static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, cons
 }
 
 // ------------------------------------------------------------------------------ decode
-int tc_decode(bvg_plan* p, const void* latent, int latent_dtype, const int32_t* h_len, const int* d_len, int B,
-              int Tmax, void* wav_out, int wav_dtype, cudaStream_t st) {
-  TcPlan* t = static_cast<TcPlan*>(p->tc);
-  if (!t) return fail(BVG_ERR_STATE, "tcgen05 path: weights not packed");
+// All activation buffers of a decode have Fs*rate rows per (utterance, channel group); `h_len` /
+// `d_len` give the valid frames per utterance.  In the time-split (shard) mode Fs is the common
+// frame stride of all ranks and the buffers are addressed through window-start pointers.
+struct StageIO {
+  const __nv_bfloat16* cur = nullptr;   // stage input, rate[i]
+  __nv_bfloat16* xin = nullptr;         // ConvTranspose output (private)
+  __nv_bfloat16* xs = nullptr;          // stage output, rate[i+1]
+  int B = 1, Fs = 0;
+  const int32_t* h_len = nullptr;
+  const int* d_len = nullptr;
+  int st_lo_f = 0, st_hi_f = 0x7fffff;  // frames of the window whose output rows are stored in xs
+  int cur_rows = 0;                     // rows of `cur` that exist behind the pointer (0 = Fs*rate[i])
+  bool concurrent = true;
+};
+
+static int tc_prepare(bvg_plan* p, TcPlan* t, int B, int Fs) {
   int rc;
-  size_t max_elems = (size_t)p->C[0] * Tmax;
+  size_t max_elems = (size_t)p->C[0] * Fs;
   for (int i = 0; i < p->n_stages; ++i)
-    max_elems = std::max(max_elems, (size_t)p->C[i + 1] * Tmax * p->rate[i + 1]);
-  if ((rc = tc_ensure_ws(p, max_elems * B * sizeof(__nv_bfloat16)))) return rc;
-  const size_t lat_need = (size_t)B * p->cfg.gpt_dim * Tmax * sizeof(__nv_bfloat16);
+    max_elems = std::max(max_elems, (size_t)p->C[i + 1] * Fs * p->rate[i + 1]);
+  const size_t buf_bytes = max_elems * B * sizeof(__nv_bfloat16);
+  if ((rc = tc_ensure_ws(p, buf_bytes))) return rc;
+  const size_t lat_need = (size_t)B * p->cfg.gpt_dim * Fs * sizeof(__nv_bfloat16);
   if (lat_need > t->lat_bytes) {
     BVG_CUDA(cudaDeviceSynchronize());
     if (t->lat_blk) BVG_CUDA(cudaFree(t->lat_blk));
@@ -376,32 +399,6 @@ int tc_decode(bvg_plan* p, const void* latent, int latent_dtype, const int32_t* 
     t->lat_bytes = lat_need;
     t->maps.clear();
   }
-  __nv_bfloat16* bufs[4] = {(__nv_bfloat16*)p->ws[0], (__nv_bfloat16*)p->ws[1], (__nv_bfloat16*)p->ws[2],
-                            (__nv_bfloat16*)p->ws[3]};
-  const CUtensorMap* map;
-
-  // latent -> blocked bf16
-  {
-    dim3 grid(ceil_div(Tmax, 128), p->cfg.gpt_dim / 8, B);
-    prof_begin(p, st, 2, 0.0, (double)B * Tmax * p->cfg.gpt_dim * 6.0);
-    k_latent_blk<<<grid, 128, 0, st>>>(latent, latent_dtype, (__nv_bfloat16*)t->lat_blk, p->cfg.gpt_dim, Tmax, d_len);
-    prof_end(p, st);
-    BVG_CUDA(cudaGetLastError());
-    ++p->last_launches;
-  }
-  // conv_pre + cond_layer add (models.py:226-228): plain conv, TMA tile feeds the MMA directly
-  __nv_bfloat16* cur = bufs[0];
-  {
-    if ((rc = get_map(t, t->lat_blk, p->cfg.gpt_dim, Tmax, B, &map))) return rc;
-    TcLaunch q;
-    q.x = t->lat_blk; q.out = cur; q.bias_b = p->condb + p->cond_off[0]; q.bias_b_stride = p->cond_total;
-    q.dil = 1; q.B = B; q.Tstride = Tmax; q.rate = 1; q.d_len = d_len; q.cls = 2;
-    q.h_len = h_len; q.sm_count = p->sm_count;
-    if ((rc = launch_tc(p, *map, t->pre, p->conv_pre, nullptr, q, st))) return rc;
-  }
-  const int nk = p->cfg.num_kernels;
-  // streams / events / per-block buffers for the concurrent AMP blocks
-  const size_t buf_bytes = max_elems * B * sizeof(__nv_bfloat16);
   if (buf_bytes > t->cbuf_bytes) {
     BVG_CUDA(cudaDeviceSynchronize());
     for (void*& qb : t->cbuf) { if (qb) BVG_CUDA(cudaFree(qb)); qb = nullptr; }
@@ -415,68 +412,369 @@ int tc_decode(bvg_plan* p, const void* latent, int latent_dtype, const int32_t* 
     BVG_CUDA(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
     for (cudaEvent_t& e : t->ev_last) BVG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
+  return 0;
+}
+
+// latent -> blocked bf16 -> conv_pre + cond_layer add (models.py:222-228)
+static int tc_pre(bvg_plan* p, TcPlan* t, const void* latent, int latent_dtype, __nv_bfloat16* out, int B, int Fs,
+                  const int32_t* h_len, const int* d_len, cudaStream_t st) {
+  int rc;
+  const CUtensorMap* map;
+  dim3 grid(ceil_div(Fs, 128), p->cfg.gpt_dim / 8, B);
+  prof_begin(p, st, 2, 0.0, (double)B * Fs * p->cfg.gpt_dim * 6.0);
+  k_latent_blk<<<grid, 128, 0, st>>>(latent, latent_dtype, (__nv_bfloat16*)t->lat_blk, p->cfg.gpt_dim, Fs, d_len);
+  prof_end(p, st);
+  BVG_CUDA(cudaGetLastError());
+  ++p->last_launches;
+  if ((rc = get_map(t, t->lat_blk, p->cfg.gpt_dim, Fs, B, &map))) return rc;
+  TcLaunch q;   // plain conv: the TMA tile feeds the MMA directly
+  q.x = t->lat_blk; q.out = out; q.bias_b = p->condb + p->cond_off[0]; q.bias_b_stride = p->cond_total;
+  q.dil = 1; q.B = B; q.Tstride = Fs; q.rate = 1; q.d_len = d_len; q.cls = 2;
+  q.h_len = h_len; q.sm_count = p->sm_count;
+  return launch_tc(p, *map, t->pre, p->conv_pre, nullptr, q, st);
+}
+
+// one upsampling stage: ConvTranspose1d + cond add, three AMP blocks, mean (models.py:230-245)
+static int tc_stage(bvg_plan* p, TcPlan* t, int i, const StageIO& io, cudaStream_t st) {
+  int rc;
+  const CUtensorMap* map;
+  const int nk = p->cfg.num_kernels;
+  const int B = io.B;
+  const int Ci = p->C[i + 1], Ri = p->rate[i + 1], Ti = io.Fs * Ri;
   // with per-launch profiling on, the blocks are serialised on the caller's stream so that the
   // CUDA-event duration of a launch is that kernel alone (bvg_plan_set_profiling)
-  const int nstreams = p->profiling ? 1 : std::min(nk, 3);
+  const int nstreams = (p->profiling || !io.concurrent) ? 1 : std::min(nk, 3);
   cudaStream_t sj[3] = {st, t->aux[0], t->aux[1]};
-  __nv_bfloat16* xin = bufs[1];
-  for (int i = 0; i < p->n_stages; ++i) {
-    const int Ci = p->C[i + 1], Ri = p->rate[i + 1], Ti = Tmax * Ri;
-    __nv_bfloat16* xs = cur;            // cur is dead once the ConvTranspose1d has consumed it
-    {
-      // ConvTranspose1d + cond add (models.py:232-236) as a (k/u)-tap implicit GEMM on the input rate
-      const int U = p->cfg.upsample_rates[i], KK = p->ups[i].K, Tin = Tmax * p->rate[i];
-      ConvW cw = p->ups[i];
-      cw.Cout = U * Ci; cw.K = KK / U;
-      TcLaunch qu;
-      qu.x = cur; qu.out = xin; qu.dil = 1; qu.B = B; qu.Tstride = Tin; qu.out_tstride = Ti; qu.rate = p->rate[i];
-      qu.d_len = d_len; qu.cls = 2; qu.up = U; qu.pad = (KK - U) / 2; qu.cphase = Ci;
-      qu.h_len = h_len; qu.sm_count = p->sm_count;
-      qu.bias_b = p->cfg.cond_in_each_up_layer ? p->condb + p->cond_off[i + 1] : nullptr;
-      qu.bias_b_stride = p->cond_total;
-      if ((rc = get_map(t, cur, p->C[i], Tin, B, &map))) return rc;
-      if ((rc = launch_tc(p, *map, t->ups[i], cw, nullptr, qu, st))) return rc;
-    }
+  {
+    // ConvTranspose1d + cond add (models.py:232-236) as a (k/u)-tap implicit GEMM on the input rate
+    const int U = p->cfg.upsample_rates[i], KK = p->ups[i].K, Tin = io.Fs * p->rate[i];
+    ConvW cw = p->ups[i];
+    cw.Cout = U * Ci; cw.K = KK / U;
+    TcLaunch qu;
+    qu.x = io.cur; qu.out = io.xin; qu.dil = 1; qu.B = B; qu.Tstride = Tin; qu.out_tstride = Ti; qu.rate = p->rate[i];
+    qu.d_len = io.d_len; qu.cls = 2; qu.up = U; qu.pad = (KK - U) / 2; qu.cphase = Ci;
+    qu.h_len = io.h_len; qu.sm_count = p->sm_count;
+    qu.bias_b = p->cfg.cond_in_each_up_layer ? p->condb + p->cond_off[i + 1] : nullptr;
+    qu.bias_b_stride = p->cond_total;
+    if ((rc = get_map(t, io.cur, p->C[i], Tin, B, &map, io.cur_rows))) return rc;
+    if ((rc = launch_tc(p, *map, t->ups[i], cw, nullptr, qu, st))) return rc;
+  }
+  if (nstreams > 1) {
     BVG_CUDA(cudaEventRecord(t->ev_fork, st));
     for (int js = 1; js < nstreams; ++js) BVG_CUDA(cudaStreamWaitEvent(sj[js], t->ev_fork, 0));
-    const int cls = (Ci >= 192) ? 0 : 1;
-    for (int j = 0; j < nk; ++j) {
-      const int n = i * nk + j;
-      cudaStream_t sq = sj[j % nstreams];
-      __nv_bfloat16* xr = (__nv_bfloat16*)t->cbuf[2 * (j % 3)];
-      __nv_bfloat16* xt = (__nv_bfloat16*)t->cbuf[2 * (j % 3) + 1];
-      const __nv_bfloat16* xcur = xin;
-      for (int m = 0; m < BVG_MAX_DIL; ++m) {
-        const int d = p->cfg.resblock_dilation_sizes[j][m];
-        TcLaunch qa;
-        qa.x = xcur; qa.out = xt; qa.dil = d; qa.B = B; qa.Tstride = Ti; qa.rate = Ri; qa.d_len = d_len; qa.cls = cls;
-        qa.h_len = h_len; qa.sm_count = p->sm_count;
-        if ((rc = get_map(t, xcur, Ci, Ti, B, &map))) return rc;
-        if ((rc = launch_tc(p, *map, t->rb1[n][m], p->rb1[n][m], &p->rba[n][2 * m], qa, sq))) return rc;
+  }
+  const int cls = (Ci >= 192) ? 0 : 1;
+  for (int j = 0; j < nk; ++j) {
+    const int n = i * nk + j;
+    cudaStream_t sq = sj[j % nstreams];
+    __nv_bfloat16* xr = (__nv_bfloat16*)t->cbuf[2 * (j % 3)];
+    __nv_bfloat16* xt = (__nv_bfloat16*)t->cbuf[2 * (j % 3) + 1];
+    const __nv_bfloat16* xcur = io.xin;
+    for (int m = 0; m < BVG_MAX_DIL; ++m) {
+      const int d = p->cfg.resblock_dilation_sizes[j][m];
+      TcLaunch qa;
+      qa.x = xcur; qa.out = xt; qa.dil = d; qa.B = B; qa.Tstride = Ti; qa.rate = Ri; qa.d_len = io.d_len; qa.cls = cls;
+      qa.h_len = io.h_len; qa.sm_count = p->sm_count;
+      if ((rc = get_map(t, xcur, Ci, Ti, B, &map))) return rc;
+      if ((rc = launch_tc(p, *map, t->rb1[n][m], p->rb1[n][m], &p->rba[n][2 * m], qa, sq))) return rc;
 
-        const bool last = (m == BVG_MAX_DIL - 1);
-        TcLaunch qb;
-        qb.x = xt; qb.resid = xcur; qb.dil = 1; qb.B = B; qb.Tstride = Ti; qb.rate = Ri; qb.d_len = d_len; qb.cls = cls;
-        qb.h_len = h_len; qb.sm_count = p->sm_count;
-        if (!last) {
-          qb.out = xr;
-        } else {
-          // running sum over the blocks (models.py:239-245) is ordered: block j adds onto block j-1
-          if (j > 0) BVG_CUDA(cudaStreamWaitEvent(sq, t->ev_last[j - 1], 0));
-          qb.out = xs;
-          qb.acc_in = (j > 0) ? xs : nullptr;
-          qb.div = (j == nk - 1) ? (float)nk : 1.f;
-        }
-        if ((rc = get_map(t, xt, Ci, Ti, B, &map))) return rc;
-        if ((rc = launch_tc(p, *map, t->rb2[n][m], p->rb2[n][m], &p->rba[n][2 * m + 1], qb, sq))) return rc;
-        if (last) BVG_CUDA(cudaEventRecord(t->ev_last[j], sq));
-        xcur = xr;
+      const bool last = (m == BVG_MAX_DIL - 1);
+      TcLaunch qb;
+      qb.x = xt; qb.resid = xcur; qb.dil = 1; qb.B = B; qb.Tstride = Ti; qb.rate = Ri; qb.d_len = io.d_len; qb.cls = cls;
+      qb.h_len = io.h_len; qb.sm_count = p->sm_count;
+      if (!last) {
+        qb.out = xr;
+      } else {
+        // running sum over the blocks (models.py:239-245) is ordered: block j adds onto block j-1
+        if (j > 0 && nstreams > 1) BVG_CUDA(cudaStreamWaitEvent(sq, t->ev_last[j - 1], 0));
+        qb.out = io.xs;
+        qb.acc_in = (j > 0) ? io.xs : nullptr;
+        qb.div = (j == nk - 1) ? (float)nk : 1.f;
+        qb.st_lo = io.st_lo_f * Ri;
+        qb.st_hi = (io.st_hi_f >= 0x7fffff) ? 0x7fffffff : io.st_hi_f * Ri;
       }
+      if ((rc = get_map(t, xt, Ci, Ti, B, &map))) return rc;
+      if ((rc = launch_tc(p, *map, t->rb2[n][m], p->rb2[n][m], &p->rba[n][2 * m + 1], qb, sq))) return rc;
+      if (last && nstreams > 1) BVG_CUDA(cudaEventRecord(t->ev_last[j], sq));
+      xcur = xr;
     }
-    BVG_CUDA(cudaStreamWaitEvent(st, t->ev_last[nk - 1], 0));    // join
-    cur = xs;
+  }
+  if (nstreams > 1) BVG_CUDA(cudaStreamWaitEvent(st, t->ev_last[nk - 1], 0));    // join
+  return 0;
+}
+
+int tc_decode(bvg_plan* p, const void* latent, int latent_dtype, const int32_t* h_len, const int* d_len, int B,
+              int Tmax, void* wav_out, int wav_dtype, cudaStream_t st) {
+  TcPlan* t = static_cast<TcPlan*>(p->tc);
+  if (!t) return fail(BVG_ERR_STATE, "tcgen05 path: weights not packed");
+  int rc;
+  if ((rc = tc_prepare(p, t, B, Tmax))) return rc;
+  __nv_bfloat16* cur = (__nv_bfloat16*)p->ws[0];
+  if ((rc = tc_pre(p, t, latent, latent_dtype, cur, B, Tmax, h_len, d_len, st))) return rc;
+  for (int i = 0; i < p->n_stages; ++i) {
+    StageIO io;
+    io.cur = cur; io.xin = (__nv_bfloat16*)p->ws[1]; io.xs = cur;   // cur is dead once the ConvTranspose1d consumed it
+    io.B = B; io.Fs = Tmax; io.h_len = h_len; io.d_len = d_len;
+    if ((rc = tc_stage(p, t, i, io, st))) return rc;
   }
   return simt_post_blk(p, cur, wav_out, wav_dtype, B, Tmax, d_len, st);
+}
+
+// ------------------------------------------------------------------------------ time split (P2P)
+// BASELINE config 5 / SURVEY §8e: one long utterance split along time over R GPUs, one process per
+// GPU.  Exchange granularity is the upsampling STAGE, not the layer: before stage i every rank
+// needs HF[i] latent-frames worth of the previous stage's output beyond its own range (enough
+// for the ConvTranspose skirt plus the 90-sample receptive field of the deepest AMP block), and
+// gets them from its neighbours' exact rows by direct peer stores over NVLink (CUDA IPC mapped
+// buffers) followed by a system-scope flag; inside a stage the window is decoded as a stand-alone
+// utterance, whose window-end artefacts stay inside the halo rows and are never stored or sent.
+// 6 exchanges per decode and ~6 % recomputed work at 8 x 7.5 s, against 39 % for whole-generator
+// overlap-recompute (bvg_decode_shard) and 108 exchanges for per-layer halos.
+constexpr int kShardMargin = 32;   // H: frames of margin on each side of the own range in every buffer
+
+struct ShardState {
+  bool ready = false;
+  bvg_shard_geom g{};
+  int Fs = 0, S = 0;
+  int HF[kMaxStages + 2] = {};     // halo frames of stage i's input (i = 0..S-1) and of post (i = S)
+  int HP = 0;                       // latent halo frames for conv_pre
+  int h_win[kMaxStages + 2] = {};   // valid frames: [0] conv_pre window, [1+i] stage i window, [1+S] post window
+  int* d_win = nullptr;
+  int* flags = nullptr;             // [2 sides][16] epochs written by the neighbours; [32] = error flag
+  void* nbr_ws[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // neighbour's ws[0], ws[1]
+  int* nbr_flags[2] = {nullptr, nullptr};
+  bool nbr_ipc[2] = {false, false};
+  void* exported_ws0 = nullptr;
+};
+
+static ShardState* shard_of(bvg_plan* p) {
+  TcPlan* t = static_cast<TcPlan*>(p->tc);
+  return t ? static_cast<ShardState*>(t->shard) : nullptr;
+}
+
+__global__ void k_halo_send(const uint4* src_l, uint4* dst_l, const uint4* src_r, uint4* dst_r, int groups,
+                            int n16, long long gstride16, int* flag_l, int* flag_r, int epoch) {
+  const bool left = blockIdx.x == 0;
+  const uint4* src = left ? src_l : src_r;
+  uint4* dst = left ? dst_l : dst_r;
+  int* flag = left ? flag_l : flag_r;
+  if (!dst) return;
+  for (long long i = threadIdx.x; i < (long long)groups * n16; i += blockDim.x) {
+    const long long g = i / n16, r = i - g * n16;
+    dst[g * gstride16 + r] = src[g * gstride16 + r];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();                       // halo rows are visible system-wide before the flag
+    *reinterpret_cast<volatile int*>(flag) = epoch;
+  }
+}
+
+__global__ void k_halo_wait(const int* flag_l, const int* flag_r, int epoch, int* err) {
+  for (int side = 0; side < 2; ++side) {
+    const volatile int* f = side == 0 ? flag_l : flag_r;
+    if (!f) continue;
+    long long spins = 0;
+    while (*f < epoch) {
+      __nanosleep(200);
+      if (++spins > 20000000LL) { *err = 1 + side; return; }   // ~4 s: give up instead of hanging the GPU
+    }
+  }
+  __threadfence_system();
+}
+
+int tc_shard_setup(bvg_plan* p, const bvg_shard_geom* g, cudaStream_t st) {
+  TcPlan* t = static_cast<TcPlan*>(p->tc);
+  if (!t) return fail(BVG_ERR_STATE, "shard setup: weights not loaded");
+  if (!t->shard) t->shard = new ShardState();
+  ShardState* s = static_cast<ShardState*>(t->shard);
+  const int S = p->n_stages, own = g->f_end - g->f_begin;
+  BVG_REQUIRE(g->f_begin >= 0 && own > 0 && g->f_end <= g->f_total, "bad shard range");
+  BVG_REQUIRE(g->own_max >= own, "own_max smaller than this shard");
+  // receptive field of one stage at its output rate: deepest AMP block
+  int kmax = 0, rows_out = 0;
+  for (int j = 0; j < p->cfg.num_kernels; ++j) kmax = std::max(kmax, p->cfg.resblock_kernel_sizes[j]);
+  for (int j = 0; j < p->cfg.num_kernels; ++j) {
+    int r = 0;
+    const int k = p->cfg.resblock_kernel_sizes[j];
+    for (int m = 0; m < BVG_MAX_DIL; ++m) r += 5 + p->cfg.resblock_dilation_sizes[j][m] * (k - 1) / 2 + 5 + (k - 1) / 2;
+    rows_out = std::max(rows_out, r);
+  }
+  for (int i = 0; i < S; ++i) {
+    const int u = p->cfg.upsample_rates[i], kk = p->cfg.upsample_kernel_sizes[i];
+    const int rows_in = (rows_out + u - 1) / u + kk / u + 1;
+    s->HF[i] = (rows_in + p->rate[i] - 1) / p->rate[i];
+  }
+  s->HF[S] = (5 + 3 + p->rate[S] - 1) / p->rate[S] + 0;      // activation_post + conv_post
+  if (s->HF[S] < 1) s->HF[S] = 1;
+  s->HP = s->HF[0] + 4;                                        // conv_pre k=7 -> 3 frames + 1 spare
+  BVG_REQUIRE(s->HP <= kShardMargin, "halo %d exceeds the buffer margin", s->HP);
+  const bool hasl = g->f_begin > 0, hasr = g->f_end < g->f_total;
+  BVG_REQUIRE(!hasl || g->own_left >= s->HP, "left neighbour shorter than the halo (%d frames)", s->HP);
+  BVG_REQUIRE(!hasr || g->own_right >= s->HP, "right neighbour shorter than the halo (%d frames)", s->HP);
+  BVG_REQUIRE(own >= s->HP, "shard shorter than the halo (%d frames)", s->HP);
+  s->g = *g; s->S = S;
+  s->Fs = g->own_max + 2 * kShardMargin;
+  s->h_win[0] = (hasl ? s->HP : 0) + own + (hasr ? s->HP : 0);
+  for (int i = 0; i <= S; ++i) s->h_win[1 + i] = (hasl ? s->HF[i] : 0) + own + (hasr ? s->HF[i] : 0);
+  int rc;
+  if ((rc = tc_prepare(p, t, 1, s->Fs))) return rc;
+  if (!s->d_win) BVG_CUDA(cudaMalloc((void**)&s->d_win, sizeof(int) * (kMaxStages + 2)));
+  if (!s->flags) {
+    BVG_CUDA(cudaMalloc((void**)&s->flags, sizeof(int) * 64));
+    BVG_CUDA(cudaMemsetAsync(s->flags, 0, sizeof(int) * 64, st));
+  }
+  BVG_CUDA(cudaMemcpyAsync(s->d_win, s->h_win, sizeof(int) * (kMaxStages + 2), cudaMemcpyHostToDevice, st));
+  BVG_CUDA(cudaStreamSynchronize(st));
+  s->exported_ws0 = p->ws[0];
+  s->ready = true;
+  return 0;
+}
+
+int tc_shard_halo_frames(bvg_plan* p) {
+  ShardState* s = shard_of(p);
+  return (s && s->ready) ? s->HP : -1;
+}
+
+int tc_shard_local_ptrs(bvg_plan* p, void** ws0, void** ws1, void** flags) {
+  ShardState* s = shard_of(p);
+  if (!s || !s->ready) return fail(BVG_ERR_STATE, "shard not set up");
+  *ws0 = p->ws[0]; *ws1 = p->ws[1]; *flags = s->flags;
+  return 0;
+}
+
+int tc_shard_export(bvg_plan* p, uint8_t* handles) {
+  ShardState* s = shard_of(p);
+  if (!s || !s->ready) return fail(BVG_ERR_STATE, "shard not set up");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  void* ptrs[3] = {p->ws[0], p->ws[1], s->flags};
+  for (int i = 0; i < 3; ++i) {
+    BVG_CUDA(cudaIpcGetMemHandle(&h, ptrs[i]));
+    memcpy(handles + 64 * i, &h, 64);
+  }
+  return 0;
+}
+
+int tc_shard_connect(bvg_plan* p, int side, const uint8_t* handles, void* ws0, void* ws1, void* flags) {
+  ShardState* s = shard_of(p);
+  if (!s || !s->ready) return fail(BVG_ERR_STATE, "shard not set up");
+  BVG_REQUIRE(side == 0 || side == 1, "side must be 0 (left) or 1 (right)");
+  if (handles) {
+    void* out[3];
+    for (int i = 0; i < 3; ++i) {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, handles + 64 * i, 64);
+      BVG_CUDA(cudaIpcOpenMemHandle(&out[i], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    ws0 = out[0]; ws1 = out[1]; flags = out[2];
+    s->nbr_ipc[side] = true;
+  }
+  s->nbr_ws[side][0] = ws0; s->nbr_ws[side][1] = ws1; s->nbr_flags[side] = (int*)flags;
+  return 0;
+}
+
+void tc_shard_free(TcPlan* t) {
+  ShardState* s = static_cast<ShardState*>(t->shard);
+  if (!s) return;
+  for (int side = 0; side < 2; ++side)
+    if (s->nbr_ipc[side]) {
+      cudaIpcCloseMemHandle(s->nbr_ws[side][0]);
+      cudaIpcCloseMemHandle(s->nbr_ws[side][1]);
+      cudaIpcCloseMemHandle(s->nbr_flags[side]);
+    }
+  if (s->d_win) cudaFree(s->d_win);
+  if (s->flags) cudaFree(s->flags);
+  delete s;
+  t->shard = nullptr;
+}
+
+// phase 0: conv_pre + stage 0 (+ send halos for stage 1); phase i in 1..S-1: [wait] stage i (+ send);
+// phase S: [wait] activation_post + conv_post + tanh, own samples -> wav_out.
+int tc_shard_run(bvg_plan* p, int phase, const void* latent, int latent_dtype, const float* spk_emb, void* wav_out,
+                 int wav_dtype, int epoch, int wait, cudaStream_t st) {
+  TcPlan* t = static_cast<TcPlan*>(p->tc);
+  ShardState* s = shard_of(p);
+  if (!s || !s->ready) return fail(BVG_ERR_STATE, "shard not set up");
+  if (p->ws[0] != s->exported_ws0)
+    return fail(BVG_ERR_STATE, "workspace was re-allocated after bvg_shard_setup; set the shard up again");
+  const int S = s->S, H = kShardMargin, Fs = s->Fs;
+  BVG_REQUIRE(phase >= 0 && phase <= S, "phase %d outside [0,%d]", phase, S);
+  const int own = s->g.f_end - s->g.f_begin;
+  const bool hasl = s->g.f_begin > 0, hasr = s->g.f_end < s->g.f_total;
+  __nv_bfloat16* buf[2] = {(__nv_bfloat16*)p->ws[0], (__nv_bfloat16*)p->ws[1]};
+  int rc;
+  p->cur_sum_frames = own;
+  if (phase == 0) {
+    BVG_REQUIRE(latent && spk_emb, "phase 0 needs the latent window and the speaker embedding");
+    p->last_launches = 0;
+    if ((rc = compute_cond_bias(p, spk_emb, 1, st))) return rc;
+    const int hlp = hasl ? s->HP : 0;
+    if ((rc = tc_pre(p, t, latent, latent_dtype, buf[0] + (size_t)(H - hlp) * 8, 1, Fs, &s->h_win[0], s->d_win, st)))
+      return rc;
+  } else if (wait && (hasl || hasr)) {
+    k_halo_wait<<<1, 1, 0, st>>>(hasl ? s->flags + phase : nullptr, hasr ? s->flags + 16 + phase : nullptr, epoch,
+                                 s->flags + 32);
+    BVG_CUDA(cudaGetLastError());
+    ++p->last_launches;
+  }
+  if (phase < S) {
+    const int i = phase;
+    const int hl = hasl ? s->HF[i] : 0;
+    StageIO io;
+    io.cur = buf[i & 1] + (size_t)(H - hl) * p->rate[i] * 8;
+    io.xin = (__nv_bfloat16*)p->ws[2];
+    io.xs = buf[(i + 1) & 1] + (size_t)(H - hl) * p->rate[i + 1] * 8;
+    io.B = 1; io.Fs = Fs; io.h_len = &s->h_win[1 + i]; io.d_len = s->d_win + 1 + i;
+    // never touch the halo rows the neighbours write; at a true sequence end keep the store range
+    // open so the zero rows past the end (conv padding for the next ConvTranspose1d) get written
+    io.st_lo_f = hl; io.st_hi_f = hasr ? hl + own : 0x7fffff;
+    io.cur_rows = (Fs - (H - hl)) * p->rate[i];
+    io.concurrent = true;
+    if ((rc = tc_stage(p, t, i, io, st))) return rc;
+    // send my boundary rows of this stage's output to the neighbours (input halo of the next phase)
+    if (hasl || hasr) {
+      const int hn = s->HF[i + 1], rho = p->rate[i + 1], groups = p->C[i + 1] / 8;
+      const long long gstride16 = (long long)Fs * rho;       // uint4 (one 16 B row) per channel group
+      const uint4* mine = reinterpret_cast<const uint4*>(buf[(i + 1) & 1]);
+      const uint4* src_l = mine + (long long)H * rho;                          // my first hn frames
+      const uint4* src_r = mine + (long long)(H + own - hn) * rho;             // my last hn frames
+      uint4 *dst_l = nullptr, *dst_r = nullptr;
+      int *fl = nullptr, *fr = nullptr;
+      if (hasl) {
+        if (!s->nbr_ws[0][0]) return fail(BVG_ERR_STATE, "left neighbour not connected");
+        dst_l = reinterpret_cast<uint4*>(s->nbr_ws[0][(i + 1) & 1]) + (long long)(H + s->g.own_left) * rho;
+        fl = s->nbr_flags[0] + 16 + (i + 1);                 // I am its RIGHT neighbour
+      }
+      if (hasr) {
+        if (!s->nbr_ws[1][0]) return fail(BVG_ERR_STATE, "right neighbour not connected");
+        dst_r = reinterpret_cast<uint4*>(s->nbr_ws[1][(i + 1) & 1]) + (long long)(H - hn) * rho;
+        fr = s->nbr_flags[1] + (i + 1);                      // I am its LEFT neighbour
+      }
+      k_halo_send<<<2, 1024, 0, st>>>(src_l, dst_l, src_r, dst_r, groups, hn * rho, gstride16, fl, fr, epoch);
+      BVG_CUDA(cudaGetLastError());
+      ++p->last_launches;
+    }
+    return 0;
+  }
+  // post
+  BVG_REQUIRE(wav_out, "final phase needs wav_out");
+  const int hl = hasl ? s->HF[S] : 0;
+  const size_t esz = wav_dtype == BVG_F32 ? 4 : 2;
+  void* tmp = p->ws[3];
+  if ((rc = simt_post_blk(p, buf[S & 1] + (size_t)(H - hl) * p->rate[S] * 8, tmp, wav_dtype, 1, Fs, s->d_win + 1 + S, st)))
+    return rc;
+  BVG_CUDA(cudaMemcpyAsync(wav_out, (const char*)tmp + (size_t)hl * p->up_total * esz, (size_t)own * p->up_total * esz,
+                           cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int tc_shard_error(bvg_plan* p) {
+  ShardState* s = shard_of(p);
+  if (!s || !s->ready) return -1;
+  int e = 0;
+  if (cudaMemcpy(&e, s->flags + 32, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+  return e;
 }
 
 // ------------------------------------------------------------------------------ per-op (tests)

@@ -12,6 +12,15 @@ int tc_amp_layer(const float* x, float* y, const float* resid, int B, int C_in, 
                  const float* w, const float* bias, int k, int dilation, int act,
                  const float* up_filter, const float* down_filter, const float* alpha,
                  const float* beta, int logscale, cudaStream_t st);
+// time-split P2P decode (decode_tc.cu)
+int tc_shard_setup(bvg_plan* p, const bvg_shard_geom* g, cudaStream_t st);
+int tc_shard_halo_frames(bvg_plan* p);
+int tc_shard_local_ptrs(bvg_plan* p, void** ws0, void** ws1, void** flags);
+int tc_shard_export(bvg_plan* p, uint8_t* handles);
+int tc_shard_connect(bvg_plan* p, int side, const uint8_t* handles, void* ws0, void* ws1, void* flags);
+int tc_shard_run(bvg_plan* p, int phase, const void* latent, int latent_dtype, const float* spk_emb, void* wav_out,
+                 int wav_dtype, int epoch, int wait, cudaStream_t st);
+int tc_shard_error(bvg_plan* p);
 // helpers implemented in bvg_api.cu (SIMT kernels reused by the tcgen05 path on the blocked layout)
 int tc_ensure_ws(bvg_plan* p, size_t bytes_per_buf);
 int simt_convtr_blk(bvg_plan* p, const void* x_blk, void* out_blk, int stage, int B, int Tmax, const int* d_len,
