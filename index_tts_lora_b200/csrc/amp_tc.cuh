@@ -37,7 +37,8 @@ constexpr int X_LEAD = 32;
 constexpr int BOXR = 160;     // TMA box rows (two boxes per channel group)
 constexpr int ZR = 336;       // z rows allocated (16 runs x 21)
 constexpr int NW_ACT = 16;    // warps 0-15 activation | 16 x-TMA | 17 weights | 18 MMA | 19 spare | 20-23 epilogue
-constexpr int NX_MAX = 3;     // x ring depth (runtime: 2 when the weight ring needs the room)
+constexpr int NX_MAX = 3;     // x ring depth
+constexpr int NZ_MAX = 4;     // z ring depth: lets the activation run ahead while an epilogue drains TMEM
 constexpr int W_STAGES_MAX = 8;
 constexpr int W_STAGE_BYTES = 16384;
 constexpr int NTHREADS = 768;
@@ -51,12 +52,12 @@ constexpr int Z_BUF_BYTES = 4 * ZR * 16;   // 21504
 constexpr int OFF_BIAS = 0;
 constexpr int OFF_PREFIX = OFF_BIAS + 2 * 256 * 4;
 constexpr int OFF_BAR = OFF_PREFIX + (MAX_B + 8) * 4;
-constexpr int NUM_BARS = 2 * NX_MAX + 4 + 2 * W_STAGES_MAX + 4;
+constexpr int NUM_BARS = 2 * NX_MAX + 2 * NZ_MAX + 2 * W_STAGES_MAX + 4;
 constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
 constexpr int OFF_X = (OFF_TMEM + 16 + 127) / 128 * 128;
 __host__ __device__ constexpr int off_z(int nx) { return OFF_X + nx * X_BUF_BYTES; }
-__host__ __device__ constexpr int off_w(int nx) { return off_z(nx) + 2 * Z_BUF_BYTES; }
-__host__ __device__ constexpr int smem_bytes(int nx, int wst) { return off_w(nx) + wst * W_STAGE_BYTES; }
+__host__ __device__ constexpr int off_w(int nx, int nz) { return off_z(nx) + nz * Z_BUF_BYTES; }
+__host__ __device__ constexpr int smem_bytes(int nx, int nz, int wst) { return off_w(nx, nz) + wst * W_STAGE_BYTES; }
 
 struct TcArgs {
   const __nv_bfloat16* wt;     // [ntile][chunk][tap][4][n_tile][8] bf16
@@ -68,7 +69,8 @@ struct TcArgs {
   __nv_bfloat16* out;          // blocked [B][Cout/8][Tstride][8]
   float div;
   int Cin, Cout, K, dil, n_tile, n_tiles, taps_per_stage;
-  int nx, wst;                 // ring depths: x buffers (2..3), weight stages (<= 8)
+  int nx, nz, wst;             // ring depths: x buffers (2..3), z buffers (2..4), weight stages (<= 8)
+  int dbg;                     // timing experiments only (BVG_DBG env): 1 = 1 of 4 MMAs per tap, 2 = 16-byte weight copies
   int st_lo, st_hi;            // conv mode: only rows in [st_lo, st_hi) are stored (time-split shards keep
                                // their hands off the halo rows that the neighbouring GPUs write)
   int B;
@@ -345,16 +347,16 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
 
   const uint32_t s_base = smem_u32(smem);
   const uint32_t bar0 = s_base + OFF_BAR;
-  const int NX = a.nx, W_STAGES = a.wst;
-  const int OFF_Z = off_z(NX), OFF_W = off_w(NX);
+  const int NX = a.nx, NZ = a.nz, W_STAGES = a.wst;
+  const int OFF_Z = off_z(NX), OFF_W = off_w(NX, NZ);
   auto BAR_XFULL = [&](int i) { return bar0 + 8 * (0 + i); };
   auto BAR_XEMPTY = [&](int i) { return bar0 + 8 * (NX_MAX + i); };
   auto BAR_ZFULL = [&](int i) { return bar0 + 8 * (2 * NX_MAX + i); };
-  auto BAR_ZEMPTY = [&](int i) { return bar0 + 8 * (2 * NX_MAX + 2 + i); };
-  auto BAR_WFULL = [&](int i) { return bar0 + 8 * (2 * NX_MAX + 4 + i); };
-  auto BAR_WEMPTY = [&](int i) { return bar0 + 8 * (2 * NX_MAX + 4 + W_STAGES_MAX + i); };
-  auto BAR_ACCFULL = [&](int i) { return bar0 + 8 * (2 * NX_MAX + 4 + 2 * W_STAGES_MAX + i); };
-  auto BAR_ACCEMPTY = [&](int i) { return bar0 + 8 * (2 * NX_MAX + 6 + 2 * W_STAGES_MAX + i); };
+  auto BAR_ZEMPTY = [&](int i) { return bar0 + 8 * (2 * NX_MAX + NZ_MAX + i); };
+  auto BAR_WFULL = [&](int i) { return bar0 + 8 * (2 * NX_MAX + 2 * NZ_MAX + i); };
+  auto BAR_WEMPTY = [&](int i) { return bar0 + 8 * (2 * NX_MAX + 2 * NZ_MAX + W_STAGES_MAX + i); };
+  auto BAR_ACCFULL = [&](int i) { return bar0 + 8 * (2 * NX_MAX + 2 * NZ_MAX + 2 * W_STAGES_MAX + i); };
+  auto BAR_ACCEMPTY = [&](int i) { return bar0 + 8 * (2 * NX_MAX + 2 * NZ_MAX + 2 * W_STAGES_MAX + 2 + i); };
   float* bias_s = reinterpret_cast<float*>(smem + OFF_BIAS);
   int* prefix = reinterpret_cast<int*>(smem + OFF_PREFIX);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM);
@@ -389,12 +391,8 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
   }
   if (warp == NW_ACT && lane == 0) {
     for (int i = 0; i < NX_MAX; ++i) { mbar_init(BAR_XFULL(i), 1); mbar_init(BAR_XEMPTY(i), ACT ? NW_ACT : 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(BAR_ZFULL(i), NW_ACT);
-      mbar_init(BAR_ZEMPTY(i), 1);
-      mbar_init(BAR_ACCFULL(i), 1);
-      mbar_init(BAR_ACCEMPTY(i), 4);
-    }
+    for (int i = 0; i < NZ_MAX; ++i) { mbar_init(BAR_ZFULL(i), NW_ACT); mbar_init(BAR_ZEMPTY(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR_ACCFULL(i), 1); mbar_init(BAR_ACCEMPTY(i), 4); }
     for (int i = 0; i < W_STAGES_MAX; ++i) { mbar_init(BAR_WFULL(i), 1); mbar_init(BAR_WEMPTY(i), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmx)) : "memory");
@@ -467,8 +465,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
             mbar_arrive(BAR_XEMPTY(xb));
           }
           if (++xb == NX) { xb = 0; xph ^= 1; }
-          zb ^= 1;
-          zph ^= (zb == 0);
+          if (++zb == NZ) { zb = 0; zph ^= 1; }
         }
       }
     }
@@ -506,7 +503,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
           for (int c = 0; c < NCH; ++c)
             for (int s = 0; s < spc; ++s) {
               const int taps = min(tps, a.K - s * tps);
-              const uint32_t bytes = (uint32_t)(taps * tile_bytes);
+              const uint32_t bytes = (a.dbg & 2) ? 16u : (uint32_t)(taps * tile_bytes);
               mbar_wait_relaxed(BAR_WEMPTY(stage), phase ^ 1, 300);
               mbar_expect_tx(BAR_WFULL(stage), bytes);
               bulk_load(s_base + OFF_W + stage * W_STAGE_BYTES, src, bytes, BAR_WFULL(stage));
@@ -549,9 +546,11 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
                 const uint32_t a0 = aU + (uint32_t)((s * tps + tj) * a.dil);
                 const uint32_t b0 = wU + (uint32_t)tj * tileU;
                 umma_bf16(tm, hiA | a0, hiB | b0, idesc, accflag);
-                umma_bf16(tm, hiA | (a0 + ksA), hiB | (b0 + ksB), idesc, 1u);
-                umma_bf16(tm + n_tile, hiA | (a0 + 128), hiB | b0, idesc, accflag);
-                umma_bf16(tm + n_tile, hiA | (a0 + 128 + ksA), hiB | (b0 + ksB), idesc, 1u);
+                if (!(a.dbg & 1)) {
+                  umma_bf16(tm, hiA | (a0 + ksA), hiB | (b0 + ksB), idesc, 1u);
+                  umma_bf16(tm + n_tile, hiA | (a0 + 128), hiB | b0, idesc, accflag);
+                  umma_bf16(tm + n_tile, hiA | (a0 + 128 + ksA), hiB | (b0 + ksB), idesc, 1u);
+                }
                 accflag = 1u;
               }
               umma_commit(BAR_WEMPTY(stage));          // weight stage free once these MMAs retire
@@ -559,8 +558,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
             }
             umma_commit(ACT ? BAR_ZEMPTY(zb) : BAR_XEMPTY(xb));
             if (++xb == NX) { xb = 0; xph ^= 1; }
-            zb ^= 1;
-            zph ^= (zb == 0);
+            if (++zb == NZ) { zb = 0; zph ^= 1; }
           }
           umma_commit(BAR_ACCFULL(as));
         }

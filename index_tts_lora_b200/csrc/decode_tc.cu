@@ -2,6 +2,7 @@
 // launch selection and the decode orchestration (models.py:212-252) on the blocked bf16 layout.
 #include <cuda.h>
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -315,7 +316,7 @@ static int launch_inst(const CUtensorMap& map, const TcArgs& a, dim3 grid, cudaS
     BVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
-  const int smem = smem_bytes(a.nx, a.wst);
+  const int smem = smem_bytes(a.nx, a.nz, a.wst);
   if (smem > 227 * 1024) return fail(BVG_ERR_STATE, "k_amp_tc smem plan %d B exceeds 227 KB", smem);
   kern<<<grid, NTHREADS, smem, st>>>(map, a);
   BVG_CUDA(cudaGetLastError());
@@ -329,14 +330,18 @@ static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, cons
   a.resid = q.resid; a.acc_in = q.acc_in; a.out = q.out; a.div = q.div;
   a.Cin = cw.Cin; a.Cout = cw.Cout; a.K = cw.K; a.dil = q.dil;
   a.n_tile = L.n_tile; a.n_tiles = L.n_tiles; a.taps_per_stage = L.tps; a.B = q.B;
-  // ring depths: layers that stream big weight tiles (16 KB per tap) are bound by the L2 latency of
-  // the weight ring, so they trade the third x buffer for 8 weight stages; narrow layers keep 3 x buffers
-  const int stage_bytes = L.tps * L.n_tile * 64;
-  if (stage_bytes * 4 > 32 * 1024) { a.nx = 2; a.wst = 8; } else { a.nx = 3; a.wst = 4; }
+  // ring depths.  Timing experiments (BVG_DBG) showed the weight stream is not the limiter (no change with
+  // 16-byte copies) while the single TMEM accumulator stage of the wide layers (4*n_tile > 512) stalls the
+  // MMAs of the next tile during the epilogue; 4 z buffers let the activation warps run ahead meanwhile.
+  a.nx = 3; a.nz = 4; a.wst = 4;
   a.Tstride = q.out_tstride ? q.out_tstride : q.Tstride;
   a.lengths = q.d_len; a.rate = q.rate; a.Tmax = q.Tstride;
   a.up = q.up; a.pad = q.pad; a.cphase = q.cphase;
   a.st_lo = q.st_lo; a.st_hi = q.st_hi;
+  {
+    static const int dbg = [] { const char* e = getenv("BVG_DBG"); return e ? atoi(e) : 0; }();
+    a.dbg = dbg;
+  }
   const int hc = q.dil * (cw.K - 1) / 2;
   a.lead = q.up ? cw.K - 1 : hc;
   if (aw) {
@@ -360,8 +365,9 @@ static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, cons
   int rc;
   // run length per activation thread: 4 warps x (8L - 6) valid rows must cover 256 + 2*hc z rows
   if (!aw) rc = launch_inst<9, false>(map, a, grid, st);
-  else if (hc <= 4) rc = launch_inst<9, true>(map, a, grid, st);
-  else rc = launch_inst<11, true>(map, a, grid, st);
+  else if (hc <= 4) rc = launch_inst<9, true>(map, a, grid, st);     // 4*(8*9-6)  = 264 >= 256 + 2*4
+  else if (hc <= 9) rc = launch_inst<10, true>(map, a, grid, st);    // 4*(8*10-6) = 296 >= 256 + 2*9 (2-way bank conflicts)
+  else rc = launch_inst<11, true>(map, a, grid, st);                 // 4*(8*11-6) = 328 >= 256 + 2*25
   prof_end(p, st);
   if (p) ++p->last_launches;
   return rc;
