@@ -9,6 +9,7 @@
 #include <tuple>
 #include <vector>
 
+#include "amp_fir.cuh"
 #include "amp_tc.cuh"
 #include "tc_api.h"
 
@@ -126,7 +127,7 @@ struct TcPlan {
   cudaStream_t aux[2] = {nullptr, nullptr};
   void* shard = nullptr;            // ShardState (time-split P2P decode)
   cudaEvent_t ev_fork = nullptr, ev_last[BVG_MAX_KERNELS] = {};
-  std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> maps;
+  std::map<std::tuple<const void*, int, int, int, int, int>, CUtensorMap> maps;
   std::vector<void*> owned;
 };
 
@@ -258,14 +259,14 @@ static PFN_encodeTiled get_encode() {
 
 // blocked bf16 activation buffer [B][C/8][Tstride][8] as a 4-D tensor {8, Tstride, C/8, B};
 // box {8, BOXR, 1, 1}; out-of-range rows / channel groups read as zero.
-static int make_map(const void* base, int C, int Tstride, int B, CUtensorMap* out, int rows = 0) {
+static int make_map(const void* base, int C, int Tstride, int B, CUtensorMap* out, int rows = 0, int box_rows = BOXR) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return fail(BVG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   // `rows` < Tstride when `base` points into the middle of a buffer (time-split windows): rows past
   // the end of the allocation are then out of bounds for the TMA unit (zero-filled, never fetched)
   cuuint64_t dims[4] = {8, (cuuint64_t)(rows > 0 ? rows : Tstride), (cuuint64_t)(C / 8), (cuuint64_t)B};
   cuuint64_t strides[3] = {16, (cuuint64_t)Tstride * 16, (cuuint64_t)(C / 8) * Tstride * 16};
-  cuuint32_t box[4] = {8, (cuuint32_t)BOXR, 1, 1};
+  cuuint32_t box[4] = {8, (cuuint32_t)box_rows, 1, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -274,13 +275,14 @@ static int make_map(const void* base, int C, int Tstride, int B, CUtensorMap* ou
   return 0;
 }
 
-static int get_map(TcPlan* t, const void* base, int C, int Tstride, int B, const CUtensorMap** out, int rows = 0) {
-  auto key = std::make_tuple(base, C, Tstride, B, rows);
+static int get_map(TcPlan* t, const void* base, int C, int Tstride, int B, const CUtensorMap** out, int rows = 0,
+                   int box_rows = BOXR) {
+  auto key = std::make_tuple(base, C, Tstride, B, rows, box_rows);
   auto it = t->maps.find(key);
   if (it == t->maps.end()) {
     if (t->maps.size() > 4096) t->maps.clear();
     CUtensorMap m;
-    int rc = make_map(base, C, Tstride, B, &m, rows);
+    int rc = make_map(base, C, Tstride, B, &m, rows, box_rows);
     if (rc) return rc;
     it = t->maps.emplace(key, m).first;
   }
@@ -323,6 +325,25 @@ static int launch_inst(const CUtensorMap& map, const TcArgs& a, dim3 grid, cudaS
   return 0;
 }
 
+template <int NUB>
+static int launch_fir_inst(const CUtensorMap& map, const TcArgs& a, dim3 grid, cudaStream_t st) {
+  auto kern = fir::k_amp_fir<NUB>;
+  static bool attr = false;
+  if (!attr) {
+    BVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fir::F_SMEM));
+    attr = true;
+  }
+  kern<<<grid, fir::NTHREADS_F, fir::F_SMEM, st>>>(map, a);
+  BVG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// narrow activated layers take k_amp_fir (up-sampling FIR on the tensor cores); BVG_FIR_MAX_C=0 disables it
+static int fir_max_c() {
+  static const int v = [] { const char* e = getenv("BVG_FIR_MAX_C"); return e ? atoi(e) : 96; }();
+  return v;
+}
+
 static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, const ConvW& cw, const ActW* aw,
                      const TcLaunch& q, cudaStream_t st) {
   TcArgs a{};
@@ -363,6 +384,19 @@ static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, cons
              samples * 2.0 * (cw.Cin + cw.Cout + (q.resid ? cw.Cout : 0) + (q.acc_in ? cw.Cout : 0)) +
                  2.0 * cw.Cin * cw.Cout * cw.K);
   int rc;
+  const bool use_fir = aw && !q.up && L.n_tiles == 1 && L.n_tile <= fir::MAX_NTILE_F && cw.Cin <= fir_max_c() &&
+                       cw.Cout <= fir_max_c() && hc <= 32;
+  if (use_fir) {
+    // x tile = 16 TMA boxes {8 channels, 96 rows} (4 time segments x 4 channel groups)
+    CUtensorMap tmp;
+    const CUtensorMap* fm = &tmp;
+    TcPlan* t = p ? static_cast<TcPlan*>(p->tc) : nullptr;
+    if (t) rc = get_map(t, q.x, cw.Cin, q.Tstride, q.B, &fm, 0, fir::XB);
+    else rc = make_map(q.x, cw.Cin, q.Tstride, q.B, &tmp, 0, fir::XB);
+    if (rc) return rc;
+    a.wst = fir::W_STAGES_F;
+    rc = (hc <= 16) ? launch_fir_inst<10>(*fm, a, grid, st) : launch_fir_inst<11>(*fm, a, grid, st);
+  } else
   // run length per activation thread: 4 warps x (8L - 6) valid rows must cover 256 + 2*hc z rows
   if (!aw) rc = launch_inst<9, false>(map, a, grid, st);
   else if (hc <= 4) rc = launch_inst<9, true>(map, a, grid, st);     // 4*(8*9-6)  = 264 >= 256 + 2*4
