@@ -37,23 +37,25 @@ using namespace tc;
 
 constexpr int NSETS = 3;
 constexpr int NW_ACT = 4 * NSETS;
-constexpr int WARP_X = NW_ACT, WARP_W = NW_ACT + 1, WARP_FIR = NW_ACT + 2, WARP_CONV = NW_ACT + 3, WARP_EPI = NW_ACT + 4;
-constexpr int NTHREADS_F = (NW_ACT + 8) * 32;   // 640
+// warps 0-11 activation | 12 x TMA | 13 weights | 14 conv MMA | 15 spare | 16-18 FIR MMA (one per set) | 19 spare | 20-23 epilogue
+constexpr int WARP_X = NW_ACT, WARP_W = NW_ACT + 1, WARP_CONV = NW_ACT + 2, WARP_FIR = NW_ACT + 4, WARP_EPI = NW_ACT + 8;
+constexpr int NTHREADS_F = (NW_ACT + 12) * 32;   // 768
 constexpr int NXF = 4, NZF = 4;          // x / z ring depths
 constexpr int XB = 96;                   // TMA box rows per (segment, channel group): S + 16 <= 96
 constexpr int X_SLOT = 16 * XB * 16;     // 24576
 constexpr int ZRF = 322;                 // z rows per channel group: >= 4*80, = 2 (mod 8) -> conflict-free 2-byte stores
 constexpr int Z_SLOT = 4 * ZRF * 16;     // 20608
 constexpr int W_STAGES_F = 2;
-constexpr int TM_D1 = 320;               // TMEM: [0, 320) conv accumulators, [320, 512) NSETS x 2 D1 slots of 32 columns
-constexpr int MAX_NTILE_F = 160;
+constexpr int NSLOT = 4;                 // D1 slots per set (MMA round trip hidden behind NSLOT - 1 blocks of snake / FIR work)
+constexpr int TM_D1 = 192;               // TMEM: [0, 192) conv accumulators, [192, 384) NSETS x NSLOT D1 slots of 16 columns
+constexpr int MAX_NTILE_F = 96;
 
 constexpr int FOFF_BIAS = 0;
 constexpr int FOFF_PREFIX = FOFF_BIAS + 2 * 256 * 4;
 constexpr int FOFF_BAR = FOFF_PREFIX + (MAX_B + 8) * 4;
-constexpr int F_NUM_BARS = 2 * NXF + 4 * NSETS + 2 * NZF + 2 * W_STAGES_F + 4;
+constexpr int F_NUM_BARS = 2 * NXF + 2 * NSLOT * NSETS + 2 * NZF + 2 * W_STAGES_F + 4;
 constexpr int FOFF_TMEM = FOFF_BAR + F_NUM_BARS * 8;
-constexpr int FOFF_UPB = (FOFF_TMEM + 16 + 127) / 128 * 128;   // [2][32][8] bf16 Toeplitz taps [hi | lo]
+constexpr int FOFF_UPB = (FOFF_TMEM + 16 + 127) / 128 * 128;   // 2 x [2][16][8] bf16 Toeplitz taps: hi split, then lo split
 constexpr int FOFF_X = FOFF_UPB + 1024;
 constexpr int FOFF_Z = FOFF_X + NXF * X_SLOT;
 constexpr int FOFF_W = FOFF_Z + NZF * Z_SLOT;
@@ -103,6 +105,166 @@ __device__ __noinline__ float fir_edge_z(const uint8_t* xrow0, int tbox0, int m,
   return z;
 }
 
+// Lean conv-mode epilogue (no ConvTranspose scatter, one column tile): TMEM -> +bias(+cond) (+resid) (+sum) (x1/div)
+// -> bf16 -> 16-byte stores.  32 accumulator columns per step with the residual / running-sum rows of the step
+// already in flight when the TMEM load is issued; packed f32x2 arithmetic.  Same store rules as epilogue_role.
+template <int NCOL>
+__device__ __forceinline__ void epi_step(const TcArgs& a, const float* bs, uint32_t taddr, int cb0, int ngs, int code,
+                                         const __nv_bfloat16* resid, const __nv_bfloat16* accin, __nv_bfloat16* outp,
+                                         int rowoff, int gstride, u64 rdiv2) {
+  constexpr int NG = NCOL / 8;
+  uint4 rr[NG], qq[NG];
+  const int o0 = (cb0 >> 3) * gstride + rowoff;
+  if (code == 1) {
+    if (resid) {
+#pragma unroll
+      for (int kk = 0; kk < NG; ++kk)      // dead groups re-read the last live one (no predicated array slots)
+        rr[kk] = *reinterpret_cast<const uint4*>(resid + o0 + min(kk, ngs - 1) * gstride);
+    }
+    if (accin) {
+#pragma unroll
+      for (int kk = 0; kk < NG; ++kk)
+        qq[kk] = *reinterpret_cast<const uint4*>(accin + o0 + min(kk, ngs - 1) * gstride);
+    }
+  }
+  uint32_t v[NCOL];
+  if constexpr (NCOL == 32) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr + (uint32_t)cb0));
+  } else {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr + (uint32_t)cb0));
+  }
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  if (code == 0) return;
+#pragma unroll
+  for (int kk = 0; kk < NG; ++kk) {
+    if (kk >= ngs) break;
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (code == 1) {
+      const ulonglong2 b01 = *reinterpret_cast<const ulonglong2*>(bs + cb0 + kk * 8);
+      const ulonglong2 b23 = *reinterpret_cast<const ulonglong2*>(bs + cb0 + kk * 8 + 4);
+      u64 f[4];
+      f[0] = add2(pk(__uint_as_float(v[kk * 8 + 0]), __uint_as_float(v[kk * 8 + 1])), b01.x);
+      f[1] = add2(pk(__uint_as_float(v[kk * 8 + 2]), __uint_as_float(v[kk * 8 + 3])), b01.y);
+      f[2] = add2(pk(__uint_as_float(v[kk * 8 + 4]), __uint_as_float(v[kk * 8 + 5])), b23.x);
+      f[3] = add2(pk(__uint_as_float(v[kk * 8 + 6]), __uint_as_float(v[kk * 8 + 7])), b23.y);
+      if (resid) {
+        f[0] = add2(f[0], bf2_to_f2(rr[kk].x)); f[1] = add2(f[1], bf2_to_f2(rr[kk].y));
+        f[2] = add2(f[2], bf2_to_f2(rr[kk].z)); f[3] = add2(f[3], bf2_to_f2(rr[kk].w));
+      }
+      if (accin) {
+        f[0] = add2(f[0], bf2_to_f2(qq[kk].x)); f[1] = add2(f[1], bf2_to_f2(qq[kk].y));
+        f[2] = add2(f[2], bf2_to_f2(qq[kk].z)); f[3] = add2(f[3], bf2_to_f2(qq[kk].w));
+      }
+      if (a.div != 1.0f) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) f[e] = mul2(f[e], rdiv2);
+      }
+      uint32_t w[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float lo, hi;
+        upk(f[e], lo, hi);
+        __nv_bfloat162 pb = __floats2bfloat162_rn(lo, hi);
+        w[e] = *reinterpret_cast<uint32_t*>(&pb);
+      }
+      o = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    *reinterpret_cast<uint4*>(outp + o0 + kk * gstride) = o;
+  }
+}
+
+__device__ __forceinline__ void epilogue_fir(const TcArgs& a, float* bias_s, const int* prefix, uint32_t bar_accfull0,
+                                             uint32_t bar_accempty0, uint32_t tmem, int nacc, int total_tiles, int q,
+                                             int lane, int etid) {
+  const int n_tile = a.n_tile;
+  const int cg_total = a.Cout >> 3;
+  const int ng = min(n_tile >> 3, cg_total);
+  const int gstride = a.Tstride * 8;
+  const float rdiv = 1.0f / a.div;
+  const u64 rdiv2 = pk(rdiv, rdiv);
+  TileCursor cur{prefix};
+  int it = 0, last_b = -1;
+  for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++it) {
+    int b, t0, nt;
+    cur.locate(w, 1, b, t0, nt);
+    const int T = a.lengths ? a.lengths[b] * a.rate : a.Tmax;
+    const int as = (nacc == 2) ? (it & 1) : 0;
+    const int ause = (nacc == 2) ? (it >> 1) : it;
+    if (last_b < 0 || (a.bias_b && b != last_b)) {                     // bias row changes with the utterance only
+      asm volatile("bar.sync 1, 128;" ::: "memory");                   // every warp is done with the previous row
+      for (int i = etid; i < n_tile; i += 128) {
+        float v = 0.f;
+        if (i < a.Cout) {
+          v = __ldg(a.bias + i);
+          if (a.bias_b) v += __ldg(a.bias_b + (size_t)b * a.bias_b_stride + i);
+        }
+        bias_s[i] = v;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      last_b = b;
+    }
+    const size_t ubase = (size_t)b * cg_total * a.Tstride * 8;
+    const __nv_bfloat16* resid = a.resid ? a.resid + ubase : nullptr;
+    const __nv_bfloat16* accin = a.acc_in ? a.acc_in + ubase : nullptr;
+    __nv_bfloat16* outp = a.out + ubase;
+    if (resid || accin) {
+      // warm L2 with this tile's residual / running-sum rows while its MMAs are still running
+#pragma unroll 1
+      for (int mb = 0; mb < 2; ++mb) {
+        const int t = t0 + mb * 128 + q * 32 + lane;
+        if (t >= T) continue;
+        int o = t * 8;
+#pragma unroll 1
+        for (int g = 0; g < ng; ++g, o += gstride) {
+          if (resid) asm volatile("prefetch.global.L2 [%0];" ::"l"(resid + o));
+          if (accin) asm volatile("prefetch.global.L2 [%0];" ::"l"(accin + o));
+        }
+      }
+    }
+    if (q == 0) mbar_wait_relaxed(bar_accfull0 + 8 * as, ause & 1, 100);
+    asm volatile("bar.sync 2, 128;" ::: "memory");
+    tc_fence_after();
+    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * n_tile);
+#pragma unroll 1
+    for (int mb = 0; mb < ((a.dbg & 8) ? 0 : 2); ++mb) {
+      const int t = t0 + mb * 128 + q * 32 + lane;
+      const int code = (t >= a.Tmax || t < a.st_lo || t >= a.st_hi) ? 0 : (t < T ? 1 : 2);
+#pragma unroll 1
+      for (int cb0 = 0; cb0 < n_tile; cb0 += 32) {
+        const int ngs = ng - (cb0 >> 3);
+        if (ngs <= 0) break;                                            // warp-uniform
+        if (n_tile - cb0 >= 32)
+          epi_step<32>(a, bias_s, taddr + (uint32_t)(mb * n_tile), cb0, ngs, code, resid, accin, outp, t * 8, gstride, rdiv2);
+        else
+          epi_step<16>(a, bias_s, taddr + (uint32_t)(mb * n_tile), cb0, ngs, code, resid, accin, outp, t * 8, gstride, rdiv2);
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_accempty0 + 8 * as);
+    // un-activated consumers (ConvTranspose1d) read one row past the end: keep rows [T, T+8) zero
+    // when the utterance ends exactly on this tile's boundary (otherwise they were zeroed above)
+    if (T == t0 + M_TILE && T < a.Tmax && T < a.st_hi && q == 0) {
+      for (int i = lane; i < ng * 8; i += 32) {
+        const int g = i >> 3, r = T + (i & 7);
+        if (r < a.Tmax)
+          *reinterpret_cast<uint4*>(a.out + (((size_t)b * cg_total + g) * a.Tstride + r) * 8) = make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
+}
+
 template <int NUB>
 __global__ void __launch_bounds__(NTHREADS_F, 1)
 k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs a) {
@@ -116,14 +278,14 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
   const uint32_t bar0 = s_base + FOFF_BAR;
   auto BAR_XFULL = [&](int i) { return bar0 + 8 * i; };
   auto BAR_XEMPTY = [&](int i) { return bar0 + 8 * (NXF + i); };
-  auto BAR_DFULL = [&](int i) { return bar0 + 8 * (2 * NXF + i); };                 // i = set*2 + slot
-  auto BAR_DEMPTY = [&](int i) { return bar0 + 8 * (2 * NXF + 2 * NSETS + i); };
-  auto BAR_ZFULL = [&](int i) { return bar0 + 8 * (2 * NXF + 4 * NSETS + i); };
-  auto BAR_ZEMPTY = [&](int i) { return bar0 + 8 * (2 * NXF + 4 * NSETS + NZF + i); };
-  auto BAR_WFULL = [&](int i) { return bar0 + 8 * (2 * NXF + 4 * NSETS + 2 * NZF + i); };
-  auto BAR_WEMPTY = [&](int i) { return bar0 + 8 * (2 * NXF + 4 * NSETS + 2 * NZF + W_STAGES_F + i); };
-  auto BAR_ACCFULL = [&](int i) { return bar0 + 8 * (2 * NXF + 4 * NSETS + 2 * NZF + 2 * W_STAGES_F + i); };
-  auto BAR_ACCEMPTY = [&](int i) { return bar0 + 8 * (2 * NXF + 4 * NSETS + 2 * NZF + 2 * W_STAGES_F + 2 + i); };
+  auto BAR_DFULL = [&](int i) { return bar0 + 8 * (2 * NXF + i); };                 // i = set*NSLOT + slot
+  auto BAR_DEMPTY = [&](int i) { return bar0 + 8 * (2 * NXF + NSLOT * NSETS + i); };
+  auto BAR_ZFULL = [&](int i) { return bar0 + 8 * (2 * NXF + 2 * NSLOT * NSETS + i); };
+  auto BAR_ZEMPTY = [&](int i) { return bar0 + 8 * (2 * NXF + 2 * NSLOT * NSETS + NZF + i); };
+  auto BAR_WFULL = [&](int i) { return bar0 + 8 * (2 * NXF + 2 * NSLOT * NSETS + 2 * NZF + i); };
+  auto BAR_WEMPTY = [&](int i) { return bar0 + 8 * (2 * NXF + 2 * NSLOT * NSETS + 2 * NZF + W_STAGES_F + i); };
+  auto BAR_ACCFULL = [&](int i) { return bar0 + 8 * (2 * NXF + 2 * NSLOT * NSETS + 2 * NZF + 2 * W_STAGES_F + i); };
+  auto BAR_ACCEMPTY = [&](int i) { return bar0 + 8 * (2 * NXF + 2 * NSLOT * NSETS + 2 * NZF + 2 * W_STAGES_F + 2 + i); };
   float* bias_s = reinterpret_cast<float*>(smem + FOFF_BIAS);
   int* prefix = reinterpret_cast<int*>(smem + FOFF_PREFIX);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + FOFF_TMEM);
@@ -157,7 +319,7 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < NXF; ++i) { mbar_init(BAR_XFULL(i), 1); mbar_init(BAR_XEMPTY(i), 5); }
-    for (int i = 0; i < 2 * NSETS; ++i) { mbar_init(BAR_DFULL(i), 1); mbar_init(BAR_DEMPTY(i), 4); }
+    for (int i = 0; i < NSLOT * NSETS; ++i) { mbar_init(BAR_DFULL(i), 1); mbar_init(BAR_DEMPTY(i), 4); }
     for (int i = 0; i < NZF; ++i) { mbar_init(BAR_ZFULL(i), 4); mbar_init(BAR_ZEMPTY(i), 1); }
     for (int i = 0; i < W_STAGES_F; ++i) { mbar_init(BAR_WFULL(i), 1); mbar_init(BAR_WEMPTY(i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(BAR_ACCFULL(i), 1); mbar_init(BAR_ACCEMPTY(i), 4); }
@@ -167,7 +329,8 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
   if (warp >= 2 && warp < 6) {
     // UP[k][cc]: u(block sample cc) = sum_k UP[k][cc] * x(box row 8*bi + k);  cc = 2i: taps up2[11-2m] at k = i+m,
     // cc = 2i+1: taps up2[10-2m] at k = i+1+m (resample.py:19-31 polyphase form, gain folded into up2).
-    // Columns: n < 8 -> even sample cc = 2n, n >= 8 -> odd sample cc = 2(n-8)+1; +16 = low-order bf16 split.
+    // Columns: n < 8 -> even sample cc = 2n, n >= 8 -> odd sample cc = 2(n-8)+1.  fp32 taps = hi + lo (two bf16
+    // MMAs accumulate into the same D1 columns: the FIR is exact to 2^-17 of a tap).
     __nv_bfloat16* upb = reinterpret_cast<__nv_bfloat16*>(smem + FOFF_UPB);
     for (int idx = (warp - 2) * 32 + lane; idx < 16 * 16; idx += 128) {
       const int k = idx >> 4, n = idx & 15;
@@ -177,8 +340,8 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
       if (m >= 0 && m < 6) v = (n < 8) ? a.up2[11 - 2 * m] : a.up2[10 - 2 * m];
       const __nv_bfloat16 hi = __float2bfloat16_rn(v);
       const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-      upb[((k >> 3) * 32 + n) * 8 + (k & 7)] = hi;
-      upb[((k >> 3) * 32 + 16 + n) * 8 + (k & 7)] = lo;
+      upb[((k >> 3) * 16 + n) * 8 + (k & 7)] = hi;
+      upb[256 + ((k >> 3) * 16 + n) * 8 + (k & 7)] = lo;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -197,14 +360,15 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
 
   if (warp < NW_ACT) {
     // ===================== activation sets =====================
-    reg_inc<120>();
+    reg_inc<104>();
     const int set = warp >> 2, q = warp & 3, g = lane >> 3, c8 = lane & 7;
     u64 dnp[12];
 #pragma unroll
     for (int j = 0; j < 12; ++j) dnp[j] = pk(a.dn[j], a.dn[j]);
-    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16) + TM_D1 + (uint32_t)(set * 64);
+    const uint32_t tlane0 = tmem + ((uint32_t)(q * 32) << 16) + TM_D1 + (uint32_t)(set * NSLOT * 16);
+    const uint32_t dfull0 = BAR_DFULL(set * NSLOT), dempty0 = BAR_DEMPTY(set * NSLOT);
     TileCursor cur{prefix};
-    int ks = 0;                                    // blocks consumed by this set (slot = ks & 1)
+    int slot = 0, sph = 0;                         // D1 slot / phase of the next block of this set
     for (int n = set; n < total_chunks; n += NSETS) {
       const int it = n / NCH, c = n - it * NCH;
       int b, t0, nt;
@@ -217,66 +381,64 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
       const bool edge = (ts - 8 < 0) || (ts + S + 8 > T);          // warp-uniform
       const int xs = n & (NXF - 1), zs = n & (NZF - 1);
       uint8_t* zrow0 = smem + FOFF_Z + zs * Z_SLOT + g * (ZRF * 16) + (q * S) * 16 + c8 * 2;
-      u64 EP[7], OP[8];
+      // Two generations of snake samples, even (E) and odd (O) up-sampled positions, 4 packed pairs each; the
+      // generations swap roles every block, so the carried window costs no register moves.  With
+      // EW[t] = E[8bi-10+t] and OW[t] = O[8bi-12+t] (segment-relative sample pairs k -> u index 2k, 2k+1):
+      //   pair EP(t) = (EW[2t], EW[2t+1]) = t < 3 ? prev[t+1] : cur[t-3],   OP(t) = t < 4 ? prev[t] : cur[t-4].
+      u64 EA[4], OA[4], EB[4], OB[4];
 #pragma unroll
-      for (int i = 0; i < 7; ++i) EP[i] = 0ull;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) OP[i] = 0ull;
-#pragma unroll
-      for (int bi = 0; bi < NUB; ++bi) {
-        const int slot = ks & 1;
-        mbar_wait(BAR_DFULL(set * 2 + slot), (ks >> 1) & 1);
+      for (int i = 0; i < 4; ++i) { EA[i] = 0ull; OA[i] = 0ull; EB[i] = 0ull; OB[i] = 0ull; }
+      auto block = [&](u64 (&Ep)[4], u64 (&Op)[4], u64 (&Ec)[4], u64 (&Oc)[4], int bi) {
+        mbar_wait(dfull0 + 8 * slot, sph);
         tc_fence_after();
-        uint32_t v[32];
+        uint32_t v[16];
         asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-            "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-            : "r"(tlane + (uint32_t)(slot * 32)));
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(tlane0 + (uint32_t)(slot * 16)));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(BAR_DEMPTY(set * 2 + slot));
-        ++ks;
-        // window shift: EP[t] pairs E[8bi-10+2t ..], OP[t] pairs O[8bi-12+2t ..]
-        EP[0] = EP[4]; EP[1] = EP[5]; EP[2] = EP[6];
-        OP[0] = OP[4]; OP[1] = OP[5]; OP[2] = OP[6]; OP[3] = OP[7];
+        if (lane == 0) mbar_arrive(dempty0 + 8 * slot);
+        if (++slot == NSLOT) { slot = 0; sph ^= 1; }
 #pragma unroll
         for (int p = 0; p < 8; ++p) {
-          // u = hi + lo, s' = u + nhb*cos(a2*u)  (two consecutive even (p < 4) or odd (p >= 4) samples)
-          const u64 u = add2(pk(__uint_as_float(v[2 * p]), __uint_as_float(v[2 * p + 1])),
-                             pk(__uint_as_float(v[16 + 2 * p]), __uint_as_float(v[16 + 2 * p + 1])));
+          // s' = u + nhb*cos(a2*u) on two consecutive even (p < 4) or odd (p >= 4) up-sampled positions
+          const u64 u = pk(__uint_as_float(v[2 * p]), __uint_as_float(v[2 * p + 1]));
           float t0f, t1f;
           upk(mul2(a2p, u), t0f, t1f);
           const u64 sv = fma2(nhbp, pk(__cosf(t0f), __cosf(t1f)), u);
-          if (p < 4) EP[3 + p] = sv; else OP[4 + (p - 4)] = sv;
+          if (p < 4) Ec[p] = sv; else Oc[p - 4] = sv;
         }
         if (bi >= 1) {
-          if (bi == 1) mbar_wait(BAR_ZEMPTY(zs), ((n / NZF) & 1) ^ 1);      // conv MMAs of this slot's previous chunk retired
+          if (bi == 1 && !(a.dbg & 16)) mbar_wait(BAR_ZEMPTY(zs), ((n / NZF) & 1) ^ 1);      // conv MMAs of this slot's previous chunk retired
+#define EPX(t) ((t) < 3 ? Ep[(t) + 1] : Ec[(t) - 3])
+#define OPX(t) ((t) < 4 ? Op[(t)] : Oc[(t) - 4])
           // rows rho = 8(bi-1) + 2a (+1): acc1[a] pairs (rho, rho+1), acc2[a] pairs (rho-1, rho)
           u64 acc1[4], acc2[5];
 #pragma unroll
           for (int aa = 0; aa < 4; ++aa) {
             u64 s1 = hbp;
 #pragma unroll
-            for (int i = 0; i < 6; i += 2) s1 = fma2(dnp[2 * i + 1], EP[aa + i / 2], s1);
+            for (int i = 0; i < 6; i += 2) s1 = fma2(dnp[2 * i + 1], EPX(aa + i / 2), s1);
 #pragma unroll
-            for (int i = 1; i < 6; i += 2) s1 = fma2(dnp[2 * i], OP[aa + (i + 1) / 2], s1);
+            for (int i = 1; i < 6; i += 2) s1 = fma2(dnp[2 * i], OPX(aa + (i + 1) / 2), s1);
             acc1[aa] = s1;
           }
 #pragma unroll
           for (int aa = 0; aa < 5; ++aa) {
-            u64 s2 = mul2(dnp[3], EP[aa]);
+            u64 s2 = mul2(dnp[3], EPX(aa));
 #pragma unroll
-            for (int i = 3; i < 6; i += 2) s2 = fma2(dnp[2 * i + 1], EP[aa + (i - 1) / 2], s2);
+            for (int i = 3; i < 6; i += 2) s2 = fma2(dnp[2 * i + 1], EPX(aa + (i - 1) / 2), s2);
 #pragma unroll
-            for (int i = 0; i < 6; i += 2) s2 = fma2(dnp[2 * i], OP[aa + i / 2], s2);
+            for (int i = 0; i < 6; i += 2) s2 = fma2(dnp[2 * i], OPX(aa + i / 2), s2);
             acc2[aa] = s2;
           }
+#undef EPX
+#undef OPX
           float z[8];
+          uint8_t* zblk = zrow0 + (bi - 1) * 128;
 #pragma unroll
           for (int aa = 0; aa < 4; ++aa) {
             float l1, h1, l2, h2, l3, h3;
@@ -296,10 +458,16 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
 #pragma unroll
           for (int r = 0; r < 8; r += 2) {
             __nv_bfloat162 o = __floats2bfloat162_rn(z[r], z[r + 1]);
-            *reinterpret_cast<__nv_bfloat16*>(zrow0 + (8 * (bi - 1) + r) * 16) = o.x;
-            *reinterpret_cast<__nv_bfloat16*>(zrow0 + (8 * (bi - 1) + r + 1) * 16) = o.y;
+            *reinterpret_cast<__nv_bfloat16*>(zblk + r * 16) = o.x;
+            *reinterpret_cast<__nv_bfloat16*>(zblk + (r + 1) * 16) = o.y;
           }
         }
+      };
+      // not fully unrolled: the two-block body (~6 KB of SASS) stays resident in the instruction cache
+#pragma unroll 1
+      for (int bi = 0; bi < NUB; bi += 2) {
+        block(EA, OA, EB, OB, bi);
+        if (bi + 1 < NUB) block(EB, OB, EA, OA, bi + 1);
       }
       if (edge) {
         // rows within 6 samples of a sequence end see the replicate clamps of the two FIRs: exact scalar redo
@@ -361,46 +529,35 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
             }
         }
       }
-    } else if (warp == WARP_FIR) {
-      // ===================== FIR MMA issuer: D1[set][slot] = X(block) * [UP_hi | UP_lo] =====================
+    } else if (warp >= WARP_FIR && warp < WARP_FIR + NSETS) {
+      // ===================== FIR MMA issuer of one set: D1[slot] = X(block) * (UP_hi + UP_lo) =====================
       if (lane == 0) {
+        const int s = warp - WARP_FIR;
         // A: MN-major SWIZZLE_NONE (LBO = stride between 8-row K groups, SBO = stride between 8-channel M groups)
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(32 >> 3) << 17) |
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(16 >> 3) << 17) |
                                ((uint32_t)(128 >> 4) << 24);
         const u64 hiA = make_sdesc(0, 128, XB * 16);
-        const u64 bdesc = make_sdesc(s_base + FOFF_UPB, 32 * 16, 128);
-        int nn[NSETS], bb[NSETS], kk[NSETS];
-#pragma unroll
-        for (int s = 0; s < NSETS; ++s) { nn[s] = s; bb[s] = 0; kk[s] = 0; }
-        int live = 0;
-#pragma unroll
-        for (int s = 0; s < NSETS; ++s) live += nn[s] < total_chunks;
-        while (live > 0) {
-          bool progressed = false;
-#pragma unroll
-          for (int s = 0; s < NSETS; ++s) {
-            if (nn[s] >= total_chunks) continue;
-            const int slot = kk[s] & 1;
-            if (!mbar_test(BAR_DEMPTY(s * 2 + slot), ((kk[s] >> 1) & 1) ^ 1)) continue;
-            const int xs = nn[s] & (NXF - 1);
-            if (bb[s] == 0 && !mbar_test(BAR_XFULL(xs), (nn[s] / NXF) & 1)) continue;
+        const u64 bhi = make_sdesc(s_base + FOFF_UPB, 16 * 16, 128), blo = make_sdesc(s_base + FOFF_UPB + 512, 16 * 16, 128);
+        const uint32_t dfull0 = BAR_DFULL(s * NSLOT), dempty0 = BAR_DEMPTY(s * NSLOT);
+        const uint32_t td0 = tmem + TM_D1 + (uint32_t)(s * NSLOT * 16);
+        int slot = 0, ph = 0;
+        for (int n = s; n < total_chunks; n += NSETS) {
+          const int xs = n & (NXF - 1);
+          mbar_wait(BAR_XFULL(xs), (n / NXF) & 1);
+          const uint32_t a0 = (s_base + FOFF_X + xs * X_SLOT) >> 4;
+#pragma unroll 1
+          for (int bi = 0; bi < NUB; ++bi) {
+            mbar_wait(dempty0 + 8 * slot, ph ^ 1);
             tc_fence_after();
-            const uint32_t a0 = (s_base + FOFF_X + xs * X_SLOT + bb[s] * 128) >> 4;
-            umma_bf16(tmem + TM_D1 + (uint32_t)((s * 2 + slot) * 32), hiA | a0, bdesc, idesc, 0u);
-            umma_commit(BAR_DFULL(s * 2 + slot));
-            ++kk[s];
-            if (++bb[s] == NUB) {
-              umma_commit(BAR_XEMPTY(xs));
-              bb[s] = 0;
-              nn[s] += NSETS;
-              if (nn[s] >= total_chunks) --live;
-            }
-            progressed = true;
+            umma_bf16(td0 + (uint32_t)(slot * 16), hiA | (a0 + bi * 8), bhi, idesc, 0u);
+            umma_bf16(td0 + (uint32_t)(slot * 16), hiA | (a0 + bi * 8), blo, idesc, 1u);
+            umma_commit(dfull0 + 8 * slot);
+            if (++slot == NSLOT) { slot = 0; ph ^= 1; }
           }
-          if (!progressed) asm volatile("nanosleep.u32 32;");
+          umma_commit(BAR_XEMPTY(xs));
         }
       }
-    } else {
+    } else if (warp == WARP_CONV) {
       // ===================== conv MMA issuer (as k_amp_tc, A = z ring) =====================
       if (lane == 0) {
         const uint32_t idesc = make_idesc_bf16(128, n_tile);
@@ -428,6 +585,7 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
               for (int tj = 0; tj < taps; ++tj) {
                 const uint32_t a0 = aU + (uint32_t)((s * tps + tj) * a.dil);
                 const uint32_t b0 = wU + (uint32_t)tj * tileU;
+                if (a.dbg & 4) continue;                 // timing experiments only
                 umma_bf16(tm, hiA | a0, hiB | b0, idesc, accflag);
                 umma_bf16(tm, hiA | (a0 + ksA), hiB | (b0 + ksB), idesc, 1u);
                 umma_bf16(tm + n_tile, hiA | (a0 + 128), hiB | b0, idesc, accflag);
@@ -445,9 +603,9 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
     }
   } else {
     // ===================== epilogue warps (shared with k_amp_tc) =====================
-    reg_dec<64>();
-    epilogue_role(a, bias_s, prefix, BAR_ACCFULL(0), BAR_ACCEMPTY(0), tmem, nacc, total_tiles, 0, warp & 3, lane,
-                  threadIdx.x - WARP_EPI * 32);
+    reg_inc<88>();
+    epilogue_fir(a, bias_s, prefix, BAR_ACCFULL(0), BAR_ACCEMPTY(0), tmem, nacc, total_tiles, warp & 3, lane,
+                 threadIdx.x - WARP_EPI * 32);
   }
   tc_fence_before();
   __syncthreads();
