@@ -1,31 +1,32 @@
-// amp_fir.cuh — the fused AMPBlock1 layer for the narrow stages (C <= 96): the 2x kaiser-sinc
-// up-sampling FIR of Activation1d runs on the tensor cores, SnakeBeta and the down-sampling FIR in
-// registers, the dilated Conv1d as the same implicit GEMM as k_amp_tc (amp_tc.cuh).
+// amp_fir.cuh — the fused AMPBlock1 layer for the narrow stages (C <= 96): BOTH kaiser-sinc FIRs of
+// Activation1d run on the tensor cores, only SnakeBeta stays on the CUDA cores; the dilated Conv1d is the
+// same implicit GEMM as k_amp_tc (amp_tc.cuh).
 //
 // Same contract as k_amp_tc<L, true>:  xt = conv_{k,d}(Activation1d(x)) [+ resid] [+ sum] [/div]
 // (indextts/BigVGAN/models.py:65-74, alias_free_torch/act.py:9-29, resample.py:10-49, filter.py:60-96).
 //
-// Why: with lane = (channel pair, row run) the FIR/snake stage of k_amp_tc costs ~35 issue slots per
-// element and bounds the narrow stages.  Here a TMEM lane is ONE channel of one time
-// segment and its columns are consecutive time samples, so
-//   * the up-sampling FIR is a banded-Toeplitz GEMM  D1[lane, 16 u-samples] = X[lane, 16 x-rows] * UP:
-//     A = the TMA-staged x tile read MN-major (channels contiguous, time = K; a block's K window is a
-//     start-address offset), B = [UP_hi | UP_lo] bf16 splits of the fp32 taps (N = 32, one MMA per block);
-//   * SnakeBeta needs no per-element parameter traffic (one channel per thread);
-//   * the down-sampling FIR runs in registers with NO cross-lane traffic (the thread holds the time
-//     series), as packed FFMA2 over naturally aligned sample pairs (two accumulator parities).
+// Why: in k_amp_tc the two 12-tap FIRs cost ~24 FMA-pipe lane-ops per element and bound the narrow stages
+// (DESIGN.md §6).  Here a TMEM lane is ONE channel of one time segment and TMEM columns are consecutive
+// time samples, so both FIRs are banded-Toeplitz GEMMs with a tiny constant B operand:
+//   up   D1[lane, 16 u] = X[lane, 16 x-rows] * UP     A = the TMA-staged x tile read MN-major from shared
+//        memory (channels contiguous, time = K; a block's K window is a start-address offset), B = bf16 hi
+//        and lo splits of the fp32 taps accumulated by two MMAs (exact to 2^-17 of a tap);
+//   down D2[lane, 16 z] = S[lane, 48 s] * DN          A = the snake output s, written to TMEM by the
+//        activation warps as fp16 pairs (tcgen05.st) and read by the MMA straight from TMEM, B = fp16 taps.
+// The activation warps only do tcgen05.ld -> s = u + nhb*cos(a2*u) -> fp16 -> tcgen05.st, and later
+// tcgen05.ld -> +hb -> bf16 -> z tile (the UMMA A operand of the conv).
 // Tile = 256 output rows x all C_out columns of one utterance; the 256 + 2*hc activated rows of a
 // 32-channel chunk are 4 time segments of S rows x 4 channel groups = 16 row groups = 128 TMEM lanes.
 // Segment q is handled by the warps with (warp & 3) == q; a set of 4 such warps owns a whole chunk and
-// NSETS chunks are in flight.  A segment is walked in NUB = S/8 + 1 blocks of 8 x-rows; block bi
-// completes z rows [8(bi-1), 8bi) of the segment.
+// NSETS chunks are in flight.  A segment is walked in NUB = S/8 + 1 u-blocks of 16 s samples (8 x rows);
+// z-block zi (16 rows from r0 = min(16 zi, S-16)) reads s columns [2 r0, 2 r0 + 48), complete after u-block r0/8 + 2.
 //
-//   warps 0-11  activation sets     tcgen05.ld D1 -> hi+lo -> snake -> down FIR -> bf16 z rows (UMMA A layout)
-//   warp 12     TMA producer        16 boxes {8 ch, 96 rows} per chunk -> x ring
-//   warp 13     weight producer     (as k_amp_tc)
-//   warp 14     FIR MMA issuer      one N=32 MMA per (set, block), D1 slots handed over by mbarriers
-//   warp 15     conv MMA issuer     (as k_amp_tc) on the z ring
-//   warps 16-19 epilogue            (shared with k_amp_tc)
+//   warps 0-7   activation sets     (2 sets x 4 TMEM lane quarters)
+//   warp 8      TMA producer        16 boxes {8 ch, 96 rows} per chunk -> x ring
+//   warp 9      weight producer     (as k_amp_tc)
+//   warp 10     conv MMA issuer     (as k_amp_tc) on the z ring
+//   warps 12,13 FIR MMA issuers     one per set: up MMAs as D1 slots free up, down MMAs as s blocks complete
+//   warps 16-19 epilogue            lean conv-mode epilogue
 // Sequence edges (replicate clamps, activations.py / filter.py) are re-evaluated exactly for the <= 12
 // affected rows per utterance by a scalar path; rows outside [0, T) are the conv's zero padding.
 #pragma once
@@ -35,28 +36,30 @@ namespace bvg {
 namespace fir {
 using namespace tc;
 
-constexpr int NSETS = 3;
+constexpr int NSETS = 2;
 constexpr int NW_ACT = 4 * NSETS;
-// warps 0-11 activation | 12 x TMA | 13 weights | 14 conv MMA | 15 spare | 16-18 FIR MMA (one per set) | 19 spare | 20-23 epilogue
-constexpr int WARP_X = NW_ACT, WARP_W = NW_ACT + 1, WARP_CONV = NW_ACT + 2, WARP_FIR = NW_ACT + 4, WARP_EPI = NW_ACT + 8;
-constexpr int NTHREADS_F = (NW_ACT + 12) * 32;   // 768
+constexpr int WARP_X = 8, WARP_W = 9, WARP_CONV = 10, WARP_FIR = 12, WARP_EPI = 16;
+constexpr int NTHREADS_F = 20 * 32;      // 640
 constexpr int NXF = 4, NZF = 4;          // x / z ring depths
 constexpr int XB = 96;                   // TMA box rows per (segment, channel group): S + 16 <= 96
 constexpr int X_SLOT = 16 * XB * 16;     // 24576
 constexpr int ZRF = 322;                 // z rows per channel group: >= 4*80, = 2 (mod 8) -> conflict-free 2-byte stores
 constexpr int Z_SLOT = 4 * ZRF * 16;     // 20608
 constexpr int W_STAGES_F = 2;
-constexpr int NSLOT = 4;                 // D1 slots per set (MMA round trip hidden behind NSLOT - 1 blocks of snake / FIR work)
-constexpr int TM_D1 = 192;               // TMEM: [0, 192) conv accumulators, [192, 384) NSETS x NSLOT D1 slots of 16 columns
+constexpr int NSLOT_MAX = 4;
 constexpr int MAX_NTILE_F = 96;
+// TMEM columns: [0, ACC) conv accumulators, then per set: NSLOT D1 slots of 16 | 2 D2 slots of 16 | 96 columns of s
+__host__ __device__ constexpr int tm_per_set(int nslot) { return 16 * nslot + 32 + 96; }
+__host__ __device__ constexpr int tm_acc(int nslot) { return 512 - NSETS * tm_per_set(nslot); }
 
 constexpr int FOFF_BIAS = 0;
 constexpr int FOFF_PREFIX = FOFF_BIAS + 2 * 256 * 4;
 constexpr int FOFF_BAR = FOFF_PREFIX + (MAX_B + 8) * 4;
-constexpr int F_NUM_BARS = 2 * NXF + 2 * NSLOT * NSETS + 2 * NZF + 2 * W_STAGES_F + 4;
+constexpr int F_NUM_BARS = 2 * NXF + 2 * NSLOT_MAX * NSETS + 4 * NSETS + 2 * NZF + 2 * W_STAGES_F + 4;
 constexpr int FOFF_TMEM = FOFF_BAR + F_NUM_BARS * 8;
-constexpr int FOFF_UPB = (FOFF_TMEM + 16 + 127) / 128 * 128;   // 2 x [2][16][8] bf16 Toeplitz taps: hi split, then lo split
-constexpr int FOFF_X = FOFF_UPB + 1024;
+constexpr int FOFF_UPB = (FOFF_TMEM + 16 + 127) / 128 * 128;   // 2 x [2][16][8] bf16 up taps (hi, lo), then [6][16][8] fp16 down taps
+constexpr int FOFF_DNB = FOFF_UPB + 1024;
+constexpr int FOFF_X = FOFF_DNB + 1536;
 constexpr int FOFF_Z = FOFF_X + NXF * X_SLOT;
 constexpr int FOFF_W = FOFF_Z + NZF * Z_SLOT;
 constexpr int F_SMEM = FOFF_W + W_STAGES_F * W_STAGE_BYTES;
@@ -265,12 +268,26 @@ __device__ __forceinline__ void epilogue_fir(const TcArgs& a, float* bias_s, con
   }
 }
 
-template <int NUB>
+__device__ __forceinline__ void umma_ts_f16(uint32_t tmem_d, uint32_t tmem_a, u64 bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ uint32_t f2_to_h2_sat(float lo, float hi) {     // {hi, lo} -> packed fp16x2, finite-saturating
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+template <int NUB, int NSLOT>
 __global__ void __launch_bounds__(NTHREADS_F, 1)
 k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int S = 8 * (NUB - 1);           // z rows per segment
-  static_assert(S + 16 <= XB && 4 * S <= ZRF, "segment geometry");
+  constexpr int NZB = (S + 15) / 16;         // z-blocks per segment (the last one may overlap its predecessor)
+  constexpr int TM_ACC = tm_acc(NSLOT), TM_SET = tm_per_set(NSLOT);
+  static_assert(S + 16 <= XB && 4 * S <= ZRF && 2 * NUB * 8 <= 192, "segment geometry");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tile = a.n_tile;
 
@@ -278,14 +295,17 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
   const uint32_t bar0 = s_base + FOFF_BAR;
   auto BAR_XFULL = [&](int i) { return bar0 + 8 * i; };
   auto BAR_XEMPTY = [&](int i) { return bar0 + 8 * (NXF + i); };
-  auto BAR_DFULL = [&](int i) { return bar0 + 8 * (2 * NXF + i); };                 // i = set*NSLOT + slot
-  auto BAR_DEMPTY = [&](int i) { return bar0 + 8 * (2 * NXF + NSLOT * NSETS + i); };
-  auto BAR_ZFULL = [&](int i) { return bar0 + 8 * (2 * NXF + 2 * NSLOT * NSETS + i); };
-  auto BAR_ZEMPTY = [&](int i) { return bar0 + 8 * (2 * NXF + 2 * NSLOT * NSETS + NZF + i); };
-  auto BAR_WFULL = [&](int i) { return bar0 + 8 * (2 * NXF + 2 * NSLOT * NSETS + 2 * NZF + i); };
-  auto BAR_WEMPTY = [&](int i) { return bar0 + 8 * (2 * NXF + 2 * NSLOT * NSETS + 2 * NZF + W_STAGES_F + i); };
-  auto BAR_ACCFULL = [&](int i) { return bar0 + 8 * (2 * NXF + 2 * NSLOT * NSETS + 2 * NZF + 2 * W_STAGES_F + i); };
-  auto BAR_ACCEMPTY = [&](int i) { return bar0 + 8 * (2 * NXF + 2 * NSLOT * NSETS + 2 * NZF + 2 * W_STAGES_F + 2 + i); };
+  auto BAR_DFULL = [&](int i) { return bar0 + 8 * (2 * NXF + i); };                              // i = set*NSLOT_MAX + slot
+  auto BAR_DEMPTY = [&](int i) { return bar0 + 8 * (2 * NXF + NSLOT_MAX * NSETS + i); };
+  auto BAR_D2FULL = [&](int i) { return bar0 + 8 * (2 * NXF + 2 * NSLOT_MAX * NSETS + i); };      // i = set*2 + slot
+  auto BAR_D2EMPTY = [&](int i) { return bar0 + 8 * (2 * NXF + 2 * NSLOT_MAX * NSETS + 2 * NSETS + i); };
+  constexpr int BZ = 2 * NXF + 2 * NSLOT_MAX * NSETS + 4 * NSETS;
+  auto BAR_ZFULL = [&](int i) { return bar0 + 8 * (BZ + i); };
+  auto BAR_ZEMPTY = [&](int i) { return bar0 + 8 * (BZ + NZF + i); };
+  auto BAR_WFULL = [&](int i) { return bar0 + 8 * (BZ + 2 * NZF + i); };
+  auto BAR_WEMPTY = [&](int i) { return bar0 + 8 * (BZ + 2 * NZF + W_STAGES_F + i); };
+  auto BAR_ACCFULL = [&](int i) { return bar0 + 8 * (BZ + 2 * NZF + 2 * W_STAGES_F + i); };
+  auto BAR_ACCEMPTY = [&](int i) { return bar0 + 8 * (BZ + 2 * NZF + 2 * W_STAGES_F + 2 + i); };
   float* bias_s = reinterpret_cast<float*>(smem + FOFF_BIAS);
   int* prefix = reinterpret_cast<int*>(smem + FOFF_PREFIX);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + FOFF_TMEM);
@@ -295,7 +315,7 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
   const int tile_bytes = n_tile * 64;
   const int tps = a.taps_per_stage;
   const int spc = (a.K + tps - 1) / tps;
-  const int nacc = (4 * n_tile <= TM_D1) ? 2 : 1;
+  const int nacc = (4 * n_tile <= TM_ACC) ? 2 : 1;
 
   // ---- prologue: tile prefix table, barriers, Toeplitz taps, TMEM
   if (warp == 0) {
@@ -319,7 +339,8 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < NXF; ++i) { mbar_init(BAR_XFULL(i), 1); mbar_init(BAR_XEMPTY(i), 5); }
-    for (int i = 0; i < NSLOT * NSETS; ++i) { mbar_init(BAR_DFULL(i), 1); mbar_init(BAR_DEMPTY(i), 4); }
+    for (int i = 0; i < NSLOT_MAX * NSETS; ++i) { mbar_init(BAR_DFULL(i), 1); mbar_init(BAR_DEMPTY(i), 4); }
+    for (int i = 0; i < 2 * NSETS; ++i) { mbar_init(BAR_D2FULL(i), 1); mbar_init(BAR_D2EMPTY(i), 4); }
     for (int i = 0; i < NZF; ++i) { mbar_init(BAR_ZFULL(i), 4); mbar_init(BAR_ZEMPTY(i), 1); }
     for (int i = 0; i < W_STAGES_F; ++i) { mbar_init(BAR_WFULL(i), 1); mbar_init(BAR_WEMPTY(i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(BAR_ACCFULL(i), 1); mbar_init(BAR_ACCEMPTY(i), 4); }
@@ -329,19 +350,26 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
   if (warp >= 2 && warp < 6) {
     // UP[k][cc]: u(block sample cc) = sum_k UP[k][cc] * x(box row 8*bi + k);  cc = 2i: taps up2[11-2m] at k = i+m,
     // cc = 2i+1: taps up2[10-2m] at k = i+1+m (resample.py:19-31 polyphase form, gain folded into up2).
-    // Columns: n < 8 -> even sample cc = 2n, n >= 8 -> odd sample cc = 2(n-8)+1.  fp32 taps = hi + lo (two bf16
-    // MMAs accumulate into the same D1 columns: the FIR is exact to 2^-17 of a tap).
+    // fp32 taps = hi + lo: two bf16 MMAs accumulate into the same D1 columns.
     __nv_bfloat16* upb = reinterpret_cast<__nv_bfloat16*>(smem + FOFF_UPB);
-    for (int idx = (warp - 2) * 32 + lane; idx < 16 * 16; idx += 128) {
+    const int t = (warp - 2) * 32 + lane;
+    for (int idx = t; idx < 16 * 16; idx += 128) {
       const int k = idx >> 4, n = idx & 15;
-      const int i = n & 7;
-      const int m = (n < 8) ? k - i : k - i - 1;
+      const int i = n >> 1;
+      const int m = (n & 1) ? k - i - 1 : k - i;
       float v = 0.f;
-      if (m >= 0 && m < 6) v = (n < 8) ? a.up2[11 - 2 * m] : a.up2[10 - 2 * m];
+      if (m >= 0 && m < 6) v = (n & 1) ? a.up2[10 - 2 * m] : a.up2[11 - 2 * m];
       const __nv_bfloat16 hi = __float2bfloat16_rn(v);
       const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
       upb[((k >> 3) * 16 + n) * 8 + (k & 7)] = hi;
       upb[256 + ((k >> 3) * 16 + n) * 8 + (k & 7)] = lo;
+    }
+    // DN[k][n]: z(row r0 + n) = hb + sum_k DN[k][n] * s(column 2 r0 + k),  DN[2n + 3 + j][n] = dn[j]  (filter.py:87-96)
+    __half* dnb = reinterpret_cast<__half*>(smem + FOFF_DNB);
+    for (int idx = t; idx < 48 * 16; idx += 128) {
+      const int k = idx >> 4, n = idx & 15;
+      const int j = k - 2 * n - 3;
+      dnb[((k >> 3) * 16 + n) * 8 + (k & 7)] = __float2half_rn((j >= 0 && j < 12) ? a.dn[j] : 0.f);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -360,15 +388,14 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
 
   if (warp < NW_ACT) {
     // ===================== activation sets =====================
-    reg_inc<104>();
     const int set = warp >> 2, q = warp & 3, g = lane >> 3, c8 = lane & 7;
-    u64 dnp[12];
-#pragma unroll
-    for (int j = 0; j < 12; ++j) dnp[j] = pk(a.dn[j], a.dn[j]);
-    const uint32_t tlane0 = tmem + ((uint32_t)(q * 32) << 16) + TM_D1 + (uint32_t)(set * NSLOT * 16);
-    const uint32_t dfull0 = BAR_DFULL(set * NSLOT), dempty0 = BAR_DEMPTY(set * NSLOT);
+    const uint32_t tset = tmem + ((uint32_t)(q * 32) << 16) + TM_ACC + (uint32_t)(set * TM_SET);
+    const uint32_t t_d1 = tset, t_d2 = tset + 16 * NSLOT, t_s = tset + 16 * NSLOT + 32;
+    const uint32_t dfull0 = BAR_DFULL(set * NSLOT_MAX), dempty0 = BAR_DEMPTY(set * NSLOT_MAX);
+    const uint32_t d2full0 = BAR_D2FULL(set * 2), d2empty0 = BAR_D2EMPTY(set * 2);
     TileCursor cur{prefix};
-    int slot = 0, sph = 0;                         // D1 slot / phase of the next block of this set
+    int slot = 0, sph = 0;                         // D1 slot / phase of the next u-block of this set
+    int dslot = 0, dph = 0;                        // D2 slot / phase of the next z-block of this set
     for (int n = set; n < total_chunks; n += NSETS) {
       const int it = n / NCH, c = n - it * NCH;
       int b, t0, nt;
@@ -377,18 +404,45 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
       const int ts = t0 - hc + q * S;              // time of this segment's z row 0
       const int ch = c * KC + g * 8 + c8;
       const float a2f = __ldg(a.a2 + ch), nhbf = __ldg(a.nhb + ch);
-      const u64 a2p = pk(a2f, a2f), nhbp = pk(nhbf, nhbf), hbp = pk(-nhbf, -nhbf);
+      const u64 a2p = pk(a2f, a2f), nhbp = pk(nhbf, nhbf);
+      const float hbf = -nhbf;
       const bool edge = (ts - 8 < 0) || (ts + S + 8 > T);          // warp-uniform
       const int xs = n & (NXF - 1), zs = n & (NZF - 1);
       uint8_t* zrow0 = smem + FOFF_Z + zs * Z_SLOT + g * (ZRF * 16) + (q * S) * 16 + c8 * 2;
-      // Two generations of snake samples, even (E) and odd (O) up-sampled positions, 4 packed pairs each; the
-      // generations swap roles every block, so the carried window costs no register moves.  With
-      // EW[t] = E[8bi-10+t] and OW[t] = O[8bi-12+t] (segment-relative sample pairs k -> u index 2k, 2k+1):
-      //   pair EP(t) = (EW[2t], EW[2t+1]) = t < 3 ? prev[t+1] : cur[t-3],   OP(t) = t < 4 ? prev[t] : cur[t-4].
-      u64 EA[4], OA[4], EB[4], OB[4];
+      // z-block zi: D2 slot -> +hb -> bf16 -> rows [r0, r0 + 16) of this segment in the z tile
+      auto extract = [&](int zi) {
+        const int r0 = (16 * zi < S - 16) ? 16 * zi : S - 16;
+        mbar_wait(d2full0 + 8 * dslot, dph);
+        tc_fence_after();
+        uint32_t v[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(t_d2 + (uint32_t)(dslot * 16)));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d2empty0 + 8 * dslot);
+        if (++dslot == 2) { dslot = 0; dph ^= 1; }
+        if (zi == 0 && !(a.dbg & 16)) mbar_wait(BAR_ZEMPTY(zs), ((n / NZF) & 1) ^ 1);   // conv MMAs of this slot's previous chunk retired
+        uint8_t* zblk = zrow0 + r0 * 16;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { EA[i] = 0ull; OA[i] = 0ull; EB[i] = 0ull; OB[i] = 0ull; }
-      auto block = [&](u64 (&Ep)[4], u64 (&Op)[4], u64 (&Ec)[4], u64 (&Oc)[4], int bi) {
+        for (int r = 0; r < 16; r += 2) {
+          float z0 = __uint_as_float(v[r]) + hbf, z1 = __uint_as_float(v[r + 1]) + hbf;
+          if (edge) {
+            const int tm_ = ts + r0 + r;
+            if (tm_ < 0 || tm_ >= T) z0 = 0.f;                    // conv zero padding (utils.py:59)
+            if (tm_ + 1 < 0 || tm_ + 1 >= T) z1 = 0.f;
+          }
+          __nv_bfloat162 o = __floats2bfloat162_rn(z0, z1);
+          *reinterpret_cast<__nv_bfloat16*>(zblk + r * 16) = o.x;
+          *reinterpret_cast<__nv_bfloat16*>(zblk + (r + 1) * 16) = o.y;
+        }
+      };
+      int znext = 0;                                // next z-block to extract
+#pragma unroll 1
+      for (int bi = 0; bi < NUB; ++bi) {
         mbar_wait(dfull0 + 8 * slot, sph);
         tc_fence_after();
         uint32_t v[16];
@@ -396,79 +450,34 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
             "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-            : "r"(tlane0 + (uint32_t)(slot * 16)));
+            : "r"(t_d1 + (uint32_t)(slot * 16)));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        uint32_t sw[8];
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+          // s' = u + nhb*cos(a2*u) on two consecutive up-sampled positions -> one fp16x2 TMEM column (even position low)
+          const u64 u = pk(__uint_as_float(v[2 * p]), __uint_as_float(v[2 * p + 1]));
+          float t0f, t1f, s0, s1;
+          upk(mul2(a2p, u), t0f, t1f);
+          upk(fma2(nhbp, pk(__cosf(t0f), __cosf(t1f)), u), s0, s1);
+          sw[p] = f2_to_h2_sat(s0, s1);
+        }
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                     ::"r"(t_s + (uint32_t)(bi * 8)), "r"(sw[0]), "r"(sw[1]), "r"(sw[2]), "r"(sw[3]), "r"(sw[4]), "r"(sw[5]),
+                       "r"(sw[6]), "r"(sw[7]) : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        // the arrival frees the D1 slot AND tells the issuer that this block's s columns are complete
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(dempty0 + 8 * slot);
         if (++slot == NSLOT) { slot = 0; sph ^= 1; }
-#pragma unroll
-        for (int p = 0; p < 8; ++p) {
-          // s' = u + nhb*cos(a2*u) on two consecutive even (p < 4) or odd (p >= 4) up-sampled positions
-          const u64 u = pk(__uint_as_float(v[2 * p]), __uint_as_float(v[2 * p + 1]));
-          float t0f, t1f;
-          upk(mul2(a2p, u), t0f, t1f);
-          const u64 sv = fma2(nhbp, pk(__cosf(t0f), __cosf(t1f)), u);
-          if (p < 4) Ec[p] = sv; else Oc[p - 4] = sv;
+        // a z-block is issued when its last u-block (r0/8 + 2) completes; pick it up one block later
+        if (znext < NZB) {
+          const int r0n = (16 * znext < S - 16) ? 16 * znext : S - 16;
+          if ((r0n >> 3) + 2 < bi) { extract(znext); ++znext; }
         }
-        if (bi >= 1) {
-          if (bi == 1 && !(a.dbg & 16)) mbar_wait(BAR_ZEMPTY(zs), ((n / NZF) & 1) ^ 1);      // conv MMAs of this slot's previous chunk retired
-#define EPX(t) ((t) < 3 ? Ep[(t) + 1] : Ec[(t) - 3])
-#define OPX(t) ((t) < 4 ? Op[(t)] : Oc[(t) - 4])
-          // rows rho = 8(bi-1) + 2a (+1): acc1[a] pairs (rho, rho+1), acc2[a] pairs (rho-1, rho)
-          u64 acc1[4], acc2[5];
-#pragma unroll
-          for (int aa = 0; aa < 4; ++aa) {
-            u64 s1 = hbp;
-#pragma unroll
-            for (int i = 0; i < 6; i += 2) s1 = fma2(dnp[2 * i + 1], EPX(aa + i / 2), s1);
-#pragma unroll
-            for (int i = 1; i < 6; i += 2) s1 = fma2(dnp[2 * i], OPX(aa + (i + 1) / 2), s1);
-            acc1[aa] = s1;
-          }
-#pragma unroll
-          for (int aa = 0; aa < 5; ++aa) {
-            u64 s2 = mul2(dnp[3], EPX(aa));
-#pragma unroll
-            for (int i = 3; i < 6; i += 2) s2 = fma2(dnp[2 * i + 1], EPX(aa + (i - 1) / 2), s2);
-#pragma unroll
-            for (int i = 0; i < 6; i += 2) s2 = fma2(dnp[2 * i], OPX(aa + i / 2), s2);
-            acc2[aa] = s2;
-          }
-#undef EPX
-#undef OPX
-          float z[8];
-          uint8_t* zblk = zrow0 + (bi - 1) * 128;
-#pragma unroll
-          for (int aa = 0; aa < 4; ++aa) {
-            float l1, h1, l2, h2, l3, h3;
-            upk(acc1[aa], l1, h1);
-            upk(acc2[aa], l2, h2);
-            upk(acc2[aa + 1], l3, h3);
-            z[2 * aa] = l1 + h2;
-            z[2 * aa + 1] = h1 + l3;
-          }
-          if (edge) {
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-              const int tm_ = ts + 8 * (bi - 1) + r;
-              if (tm_ < 0 || tm_ >= T) z[r] = 0.f;             // conv zero padding (utils.py:59)
-            }
-          }
-#pragma unroll
-          for (int r = 0; r < 8; r += 2) {
-            __nv_bfloat162 o = __floats2bfloat162_rn(z[r], z[r + 1]);
-            *reinterpret_cast<__nv_bfloat16*>(zblk + r * 16) = o.x;
-            *reinterpret_cast<__nv_bfloat16*>(zblk + (r + 1) * 16) = o.y;
-          }
-        }
-      };
-      // not fully unrolled: the two-block body (~6 KB of SASS) stays resident in the instruction cache
-#pragma unroll 1
-      for (int bi = 0; bi < NUB; bi += 2) {
-        block(EA, OA, EB, OB, bi);
-        if (bi + 1 < NUB) block(EB, OB, EA, OA, bi + 1);
       }
+      while (znext < NZB) { extract(znext); ++znext; }
       if (edge) {
         // rows within 6 samples of a sequence end see the replicate clamps of the two FIRs: exact scalar redo
         __syncwarp();
@@ -493,7 +502,6 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
       }
     }
   } else if (warp < WARP_EPI) {
-    reg_dec<40>();
     if (warp == WARP_X) {
       // ===================== x producer (TMA): 16 boxes (segment, channel group) per chunk =====================
       if (lane == 0) {
@@ -530,31 +538,60 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
         }
       }
     } else if (warp >= WARP_FIR && warp < WARP_FIR + NSETS) {
-      // ===================== FIR MMA issuer of one set: D1[slot] = X(block) * (UP_hi + UP_lo) =====================
+      // ===================== FIR MMA issuer of one set =====================
       if (lane == 0) {
         const int s = warp - WARP_FIR;
-        // A: MN-major SWIZZLE_NONE (LBO = stride between 8-row K groups, SBO = stride between 8-channel M groups)
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(16 >> 3) << 17) |
-                               ((uint32_t)(128 >> 4) << 24);
+        // up: A = x tile, MN-major SWIZZLE_NONE (LBO = stride between 8-row K groups, SBO = stride between 8-channel
+        // M groups), bf16; down: A = s in TMEM (fp16 pairs per column), B = fp16 taps
+        const uint32_t idesc_up = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(16 >> 3) << 17) |
+                                  ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc_dn = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const u64 hiA = make_sdesc(0, 128, XB * 16);
         const u64 bhi = make_sdesc(s_base + FOFF_UPB, 16 * 16, 128), blo = make_sdesc(s_base + FOFF_UPB + 512, 16 * 16, 128);
-        const uint32_t dfull0 = BAR_DFULL(s * NSLOT), dempty0 = BAR_DEMPTY(s * NSLOT);
-        const uint32_t td0 = tmem + TM_D1 + (uint32_t)(s * NSLOT * 16);
-        int slot = 0, ph = 0;
+        const u64 bdn = make_sdesc(s_base + FOFF_DNB, 16 * 16, 128);
+        const uint32_t dfull0 = BAR_DFULL(s * NSLOT_MAX), dempty0 = BAR_DEMPTY(s * NSLOT_MAX);
+        const uint32_t d2full0 = BAR_D2FULL(s * 2), d2empty0 = BAR_D2EMPTY(s * 2);
+        const uint32_t tset = tmem + TM_ACC + (uint32_t)(s * TM_SET);
+        const uint32_t t_d1 = tset, t_d2 = tset + 16 * NSLOT, t_s = tset + 16 * NSLOT + 32;
+        int slot = 0, ph = 0, dslot = 0, dph = 0;
+        // u-block cb of the current segment walk is complete (s columns written): issue the z-block it finishes
+        auto down_after = [&](int cb) {
+          int r0;
+          if (cb == NUB - 1) r0 = S - 16;
+          else if (cb >= 2 && !(cb & 1) && 8 * (cb - 2) < S - 16) r0 = 8 * (cb - 2);
+          else return;
+          mbar_wait(d2empty0 + 8 * dslot, dph ^ 1);
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < 3; ++ks)
+            umma_ts_f16(t_d2 + (uint32_t)(dslot * 16), t_s + (uint32_t)(r0 + ks * 8), bdn + (u64)(ks * 32), idesc_dn, ks > 0);
+          umma_commit(d2full0 + 8 * dslot);
+          if (++dslot == 2) { dslot = 0; dph ^= 1; }
+        };
+        int gb = 0;                                   // u-blocks issued so far by this set
         for (int n = s; n < total_chunks; n += NSETS) {
           const int xs = n & (NXF - 1);
           mbar_wait(BAR_XFULL(xs), (n / NXF) & 1);
           const uint32_t a0 = (s_base + FOFF_X + xs * X_SLOT) >> 4;
 #pragma unroll 1
-          for (int bi = 0; bi < NUB; ++bi) {
-            mbar_wait(dempty0 + 8 * slot, ph ^ 1);
+          for (int bi = 0; bi < NUB; ++bi, ++gb) {
+            mbar_wait(dempty0 + 8 * slot, ph ^ 1);    // u-block gb - NSLOT is complete (loaded, snaked, s written)
             tc_fence_after();
-            umma_bf16(td0 + (uint32_t)(slot * 16), hiA | (a0 + bi * 8), bhi, idesc, 0u);
-            umma_bf16(td0 + (uint32_t)(slot * 16), hiA | (a0 + bi * 8), blo, idesc, 1u);
+            if (gb >= NSLOT) down_after(bi >= NSLOT ? bi - NSLOT : bi - NSLOT + NUB);
+            umma_bf16(t_d1 + (uint32_t)(slot * 16), hiA | (a0 + bi * 8), bhi, idesc_up, 0u);
+            umma_bf16(t_d1 + (uint32_t)(slot * 16), hiA | (a0 + bi * 8), blo, idesc_up, 1u);
             umma_commit(dfull0 + 8 * slot);
             if (++slot == NSLOT) { slot = 0; ph ^= 1; }
           }
           umma_commit(BAR_XEMPTY(xs));
+        }
+        // drain: the last NSLOT u-blocks of the last chunk
+        const int tail = gb < NSLOT ? gb : NSLOT;
+        for (int i = 0; i < tail; ++i) {
+          mbar_wait(dempty0 + 8 * slot, ph ^ 1);
+          tc_fence_after();
+          down_after(NUB - tail + i);
+          if (++slot == NSLOT) { slot = 0; ph ^= 1; }
         }
       }
     } else if (warp == WARP_CONV) {
@@ -602,8 +639,7 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
       }
     }
   } else {
-    // ===================== epilogue warps (shared with k_amp_tc) =====================
-    reg_inc<88>();
+    // ===================== epilogue warps =====================
     epilogue_fir(a, bias_s, prefix, BAR_ACCFULL(0), BAR_ACCEMPTY(0), tmem, nacc, total_tiles, warp & 3, lane,
                  threadIdx.x - WARP_EPI * 32);
   }

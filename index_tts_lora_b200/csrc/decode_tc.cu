@@ -325,9 +325,9 @@ static int launch_inst(const CUtensorMap& map, const TcArgs& a, dim3 grid, cudaS
   return 0;
 }
 
-template <int NUB>
+template <int NUB, int NSLOT>
 static int launch_fir_inst(const CUtensorMap& map, const TcArgs& a, dim3 grid, cudaStream_t st) {
-  auto kern = fir::k_amp_fir<NUB>;
+  auto kern = fir::k_amp_fir<NUB, NSLOT>;
   static bool attr = false;
   if (!attr) {
     BVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fir::F_SMEM));
@@ -395,7 +395,11 @@ static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, cons
     else rc = make_map(q.x, cw.Cin, q.Tstride, q.B, &tmp, 0, fir::XB);
     if (rc) return rc;
     a.wst = fir::W_STAGES_F;
-    rc = (hc <= 16) ? launch_fir_inst<10>(*fm, a, grid, st) : launch_fir_inst<11>(*fm, a, grid, st);
+    // D1 slots per set: 4 when the conv accumulators leave room in TMEM (2 * n_tile <= 128 columns), else 2
+    if (2 * L.n_tile <= fir::tm_acc(4))
+      rc = (hc <= 16) ? launch_fir_inst<10, 4>(*fm, a, grid, st) : launch_fir_inst<11, 4>(*fm, a, grid, st);
+    else
+      rc = (hc <= 16) ? launch_fir_inst<10, 2>(*fm, a, grid, st) : launch_fir_inst<11, 2>(*fm, a, grid, st);
   } else
   // run length per activation thread: 4 warps x (8L - 6) valid rows must cover 256 + 2*hc z rows
   if (!aw) rc = launch_inst<9, false>(map, a, grid, st);
