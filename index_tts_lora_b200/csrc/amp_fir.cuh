@@ -21,12 +21,12 @@
 // NSETS chunks are in flight.  A segment is walked in NUB = S/8 + 1 u-blocks of 16 s samples (8 x rows);
 // z-block zi (16 rows from r0 = min(16 zi, S-16)) reads s columns [2 r0, 2 r0 + 48), complete after u-block r0/8 + 2.
 //
-//   warps 0-7   activation sets     (2 sets x 4 TMEM lane quarters)
-//   warp 8      TMA producer        16 boxes {8 ch, 96 rows} per chunk -> x ring
-//   warp 9      weight producer     (as k_amp_tc)
-//   warp 10     conv MMA issuer     (as k_amp_tc) on the z ring
-//   warps 12,13 FIR MMA issuers     one per set: up MMAs as D1 slots free up, down MMAs as s blocks complete
-//   warps 16-19 epilogue            lean conv-mode epilogue
+//   warps 0-15  activation sets     (2 sets x 2 alternating warps x 4 TMEM lane quarters)
+//   warp 16     lane 0: TMA producer, 16 boxes {8 ch, 96 rows} per chunk -> x ring; lane 1: weight producer (as k_amp_tc)
+//   warp 17     conv MMA issuer     (as k_amp_tc) on the z ring
+//   warps 18,19 up-FIR MMA issuers  one per set: two MMAs per u-block as D1 slots free up
+//   warps 20,21 down-FIR issuers    one per set: three MMAs per z-block as its s columns complete
+//   warps 22-25 epilogue            lean conv-mode epilogue
 // Sequence edges (replicate clamps, activations.py / filter.py) are re-evaluated exactly for the <= 12
 // affected rows per utterance by a scalar path; rows outside [0, T) are the conv's zero padding.
 #pragma once
@@ -36,10 +36,11 @@ namespace bvg {
 namespace fir {
 using namespace tc;
 
-constexpr int NSETS = 2;
-constexpr int NW_ACT = 4 * NSETS;
-constexpr int WARP_X = 8, WARP_W = 9, WARP_CONV = 10, WARP_FIR = 12, WARP_EPI = 16;
-constexpr int NTHREADS_F = 20 * 32;      // 640
+constexpr int NSETS = 2;                 // chunks in flight
+constexpr int NR = 2;                    // warps per (set, TMEM lane quarter), alternating blocks
+constexpr int NW_ACT = 4 * NR * NSETS;   // 16
+constexpr int WARP_XW = NW_ACT, WARP_CONV = NW_ACT + 1, WARP_UP = NW_ACT + 2, WARP_DN = WARP_UP + NSETS, WARP_EPI = WARP_DN + NSETS;
+constexpr int NTHREADS_F = (WARP_EPI + 4) * 32;      // 832
 constexpr int NXF = 4, NZF = 4;          // x / z ring depths
 constexpr int XB = 96;                   // TMA box rows per (segment, channel group): S + 16 <= 96
 constexpr int X_SLOT = 16 * XB * 16;     // 24576
@@ -55,7 +56,7 @@ __host__ __device__ constexpr int tm_acc(int nslot) { return 512 - NSETS * tm_pe
 constexpr int FOFF_BIAS = 0;
 constexpr int FOFF_PREFIX = FOFF_BIAS + 2 * 256 * 4;
 constexpr int FOFF_BAR = FOFF_PREFIX + (MAX_B + 8) * 4;
-constexpr int F_NUM_BARS = 2 * NXF + 2 * NSLOT_MAX * NSETS + 4 * NSETS + 2 * NZF + 2 * W_STAGES_F + 4;
+constexpr int F_NUM_BARS = 2 * NXF + 2 * NSLOT_MAX * NSETS + 4 * NSETS + 4 * NSETS + 2 * NZF + 2 * W_STAGES_F + 4;
 constexpr int FOFF_TMEM = FOFF_BAR + F_NUM_BARS * 8;
 constexpr int FOFF_UPB = (FOFF_TMEM + 16 + 127) / 128 * 128;   // 2 x [2][16][8] bf16 up taps (hi, lo), then [6][16][8] fp16 down taps
 constexpr int FOFF_DNB = FOFF_UPB + 1024;
@@ -111,20 +112,20 @@ __device__ __noinline__ float fir_edge_z(const uint8_t* xrow0, int tbox0, int m,
 // Lean conv-mode epilogue (no ConvTranspose scatter, one column tile): TMEM -> +bias(+cond) (+resid) (+sum) (x1/div)
 // -> bf16 -> 16-byte stores.  32 accumulator columns per step with the residual / running-sum rows of the step
 // already in flight when the TMEM load is issued; packed f32x2 arithmetic.  Same store rules as epilogue_role.
-template <int NCOL>
+template <int NCOL, bool HAS_R, bool HAS_Q>
 __device__ __forceinline__ void epi_step(const TcArgs& a, const float* bs, uint32_t taddr, int cb0, int ngs, int code,
                                          const __nv_bfloat16* resid, const __nv_bfloat16* accin, __nv_bfloat16* outp,
                                          int rowoff, int gstride, u64 rdiv2) {
   constexpr int NG = NCOL / 8;
-  uint4 rr[NG], qq[NG];
+  uint4 rr[HAS_R ? NG : 1], qq[HAS_Q ? NG : 1];
   const int o0 = (cb0 >> 3) * gstride + rowoff;
   if (code == 1) {
-    if (resid) {
+    if constexpr (HAS_R) {
 #pragma unroll
       for (int kk = 0; kk < NG; ++kk)      // dead groups re-read the last live one (no predicated array slots)
         rr[kk] = *reinterpret_cast<const uint4*>(resid + o0 + min(kk, ngs - 1) * gstride);
     }
-    if (accin) {
+    if constexpr (HAS_Q) {
 #pragma unroll
       for (int kk = 0; kk < NG; ++kk)
         qq[kk] = *reinterpret_cast<const uint4*>(accin + o0 + min(kk, ngs - 1) * gstride);
@@ -161,11 +162,11 @@ __device__ __forceinline__ void epi_step(const TcArgs& a, const float* bs, uint3
       f[1] = add2(pk(__uint_as_float(v[kk * 8 + 2]), __uint_as_float(v[kk * 8 + 3])), b01.y);
       f[2] = add2(pk(__uint_as_float(v[kk * 8 + 4]), __uint_as_float(v[kk * 8 + 5])), b23.x);
       f[3] = add2(pk(__uint_as_float(v[kk * 8 + 6]), __uint_as_float(v[kk * 8 + 7])), b23.y);
-      if (resid) {
+      if constexpr (HAS_R) {
         f[0] = add2(f[0], bf2_to_f2(rr[kk].x)); f[1] = add2(f[1], bf2_to_f2(rr[kk].y));
         f[2] = add2(f[2], bf2_to_f2(rr[kk].z)); f[3] = add2(f[3], bf2_to_f2(rr[kk].w));
       }
-      if (accin) {
+      if constexpr (HAS_Q) {
         f[0] = add2(f[0], bf2_to_f2(qq[kk].x)); f[1] = add2(f[1], bf2_to_f2(qq[kk].y));
         f[2] = add2(f[2], bf2_to_f2(qq[kk].z)); f[3] = add2(f[3], bf2_to_f2(qq[kk].w));
       }
@@ -187,7 +188,8 @@ __device__ __forceinline__ void epi_step(const TcArgs& a, const float* bs, uint3
   }
 }
 
-__device__ __forceinline__ void epilogue_fir(const TcArgs& a, float* bias_s, const int* prefix, uint32_t bar_accfull0,
+template <bool HAS_R, bool HAS_Q>
+__device__ __forceinline__ void epilogue_fir_t(const TcArgs& a, float* bias_s, const int* prefix, uint32_t bar_accfull0,
                                              uint32_t bar_accempty0, uint32_t tmem, int nacc, int total_tiles, int q,
                                              int lane, int etid) {
   const int n_tile = a.n_tile;
@@ -244,13 +246,14 @@ __device__ __forceinline__ void epilogue_fir(const TcArgs& a, float* bias_s, con
       const int t = t0 + mb * 128 + q * 32 + lane;
       const int code = (t >= a.Tmax || t < a.st_lo || t >= a.st_hi) ? 0 : (t < T ? 1 : 2);
 #pragma unroll 1
-      for (int cb0 = 0; cb0 < n_tile; cb0 += 32) {
+      constexpr int STEP = HAS_Q ? 16 : 32;       // the running-sum variant keeps fewer rows in flight (registers)
+      for (int cb0 = 0; cb0 < n_tile; cb0 += STEP) {
         const int ngs = ng - (cb0 >> 3);
         if (ngs <= 0) break;                                            // warp-uniform
-        if (n_tile - cb0 >= 32)
-          epi_step<32>(a, bias_s, taddr + (uint32_t)(mb * n_tile), cb0, ngs, code, resid, accin, outp, t * 8, gstride, rdiv2);
+        if (n_tile - cb0 >= STEP)
+          epi_step<STEP, HAS_R, HAS_Q>(a, bias_s, taddr + (uint32_t)(mb * n_tile), cb0, ngs, code, resid, accin, outp, t * 8, gstride, rdiv2);
         else
-          epi_step<16>(a, bias_s, taddr + (uint32_t)(mb * n_tile), cb0, ngs, code, resid, accin, outp, t * 8, gstride, rdiv2);
+          epi_step<16, HAS_R, HAS_Q>(a, bias_s, taddr + (uint32_t)(mb * n_tile), cb0, ngs, code, resid, accin, outp, t * 8, gstride, rdiv2);
       }
     }
     tc_fence_before();
@@ -265,6 +268,18 @@ __device__ __forceinline__ void epilogue_fir(const TcArgs& a, float* bias_s, con
           *reinterpret_cast<uint4*>(a.out + (((size_t)b * cg_total + g) * a.Tstride + r) * 8) = make_uint4(0, 0, 0, 0);
       }
     }
+  }
+}
+
+__device__ __forceinline__ void epilogue_fir(const TcArgs& a, float* bias_s, const int* prefix, uint32_t bar_accfull0,
+                                             uint32_t bar_accempty0, uint32_t tmem, int nacc, int total_tiles, int q,
+                                             int lane, int etid) {
+  if (a.resid) {
+    if (a.acc_in) epilogue_fir_t<true, true>(a, bias_s, prefix, bar_accfull0, bar_accempty0, tmem, nacc, total_tiles, q, lane, etid);
+    else epilogue_fir_t<true, false>(a, bias_s, prefix, bar_accfull0, bar_accempty0, tmem, nacc, total_tiles, q, lane, etid);
+  } else {
+    if (a.acc_in) epilogue_fir_t<false, true>(a, bias_s, prefix, bar_accfull0, bar_accempty0, tmem, nacc, total_tiles, q, lane, etid);
+    else epilogue_fir_t<false, false>(a, bias_s, prefix, bar_accfull0, bar_accempty0, tmem, nacc, total_tiles, q, lane, etid);
   }
 }
 
@@ -299,7 +314,8 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
   auto BAR_DEMPTY = [&](int i) { return bar0 + 8 * (2 * NXF + NSLOT_MAX * NSETS + i); };
   auto BAR_D2FULL = [&](int i) { return bar0 + 8 * (2 * NXF + 2 * NSLOT_MAX * NSETS + i); };      // i = set*2 + slot
   auto BAR_D2EMPTY = [&](int i) { return bar0 + 8 * (2 * NXF + 2 * NSLOT_MAX * NSETS + 2 * NSETS + i); };
-  constexpr int BZ = 2 * NXF + 2 * NSLOT_MAX * NSETS + 4 * NSETS;
+  auto BAR_SFULL = [&](int i) { return bar0 + 8 * (2 * NXF + 2 * NSLOT_MAX * NSETS + 4 * NSETS + i); };        // i = set*4 + (block & 3)
+  constexpr int BZ = 2 * NXF + 2 * NSLOT_MAX * NSETS + 4 * NSETS + 4 * NSETS;
   auto BAR_ZFULL = [&](int i) { return bar0 + 8 * (BZ + i); };
   auto BAR_ZEMPTY = [&](int i) { return bar0 + 8 * (BZ + NZF + i); };
   auto BAR_WFULL = [&](int i) { return bar0 + 8 * (BZ + 2 * NZF + i); };
@@ -338,10 +354,11 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
     if (lane == 0) prefix[0] = 0;
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < NXF; ++i) { mbar_init(BAR_XFULL(i), 1); mbar_init(BAR_XEMPTY(i), 5); }
+    for (int i = 0; i < NXF; ++i) { mbar_init(BAR_XFULL(i), 1); mbar_init(BAR_XEMPTY(i), 1 + 4 * NR); }
     for (int i = 0; i < NSLOT_MAX * NSETS; ++i) { mbar_init(BAR_DFULL(i), 1); mbar_init(BAR_DEMPTY(i), 4); }
     for (int i = 0; i < 2 * NSETS; ++i) { mbar_init(BAR_D2FULL(i), 1); mbar_init(BAR_D2EMPTY(i), 4); }
-    for (int i = 0; i < NZF; ++i) { mbar_init(BAR_ZFULL(i), 4); mbar_init(BAR_ZEMPTY(i), 1); }
+    for (int i = 0; i < 4 * NSETS; ++i) mbar_init(BAR_SFULL(i), 4);
+    for (int i = 0; i < NZF; ++i) { mbar_init(BAR_ZFULL(i), 4 * NR); mbar_init(BAR_ZEMPTY(i), 1); }
     for (int i = 0; i < W_STAGES_F; ++i) { mbar_init(BAR_WFULL(i), 1); mbar_init(BAR_WEMPTY(i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(BAR_ACCFULL(i), 1); mbar_init(BAR_ACCEMPTY(i), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -388,15 +405,17 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
 
   if (warp < NW_ACT) {
     // ===================== activation sets =====================
-    const int set = warp >> 2, q = warp & 3, g = lane >> 3, c8 = lane & 7;
+    // warp = (set, r, q): q = TMEM lane quarter = time segment, r = one of the NR warps that share the quarter and
+    // take the set's u-blocks / z-blocks alternately (global block parity), so slots and phases follow from the
+    // block counters alone and no state is carried between blocks.
+    const int set = warp / (4 * NR), r = (warp >> 2) % NR, q = warp & 3, g = lane >> 3, c8 = lane & 7;
     const uint32_t tset = tmem + ((uint32_t)(q * 32) << 16) + TM_ACC + (uint32_t)(set * TM_SET);
     const uint32_t t_d1 = tset, t_d2 = tset + 16 * NSLOT, t_s = tset + 16 * NSLOT + 32;
     const uint32_t dfull0 = BAR_DFULL(set * NSLOT_MAX), dempty0 = BAR_DEMPTY(set * NSLOT_MAX);
-    const uint32_t d2full0 = BAR_D2FULL(set * 2), d2empty0 = BAR_D2EMPTY(set * 2);
+    const uint32_t d2full0 = BAR_D2FULL(set * 2), d2empty0 = BAR_D2EMPTY(set * 2), sfull0 = BAR_SFULL(set * 4);
     TileCursor cur{prefix};
-    int slot = 0, sph = 0;                         // D1 slot / phase of the next u-block of this set
-    int dslot = 0, dph = 0;                        // D2 slot / phase of the next z-block of this set
-    for (int n = set; n < total_chunks; n += NSETS) {
+    int jc = 0;                                    // chunks of this set processed so far
+    for (int n = set; n < total_chunks; n += NSETS, ++jc) {
       const int it = n / NCH, c = n - it * NCH;
       int b, t0, nt;
       cur.locate((int)blockIdx.x + it * (int)gridDim.x, 1, b, t0, nt);
@@ -409,10 +428,14 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
       const bool edge = (ts - 8 < 0) || (ts + S + 8 > T);          // warp-uniform
       const int xs = n & (NXF - 1), zs = n & (NZF - 1);
       uint8_t* zrow0 = smem + FOFF_Z + zs * Z_SLOT + g * (ZRF * 16) + (q * S) * 16 + c8 * 2;
+      const uint8_t* xrow0 = smem + FOFF_X + xs * X_SLOT + (q * 4 + g) * (XB * 16) + c8 * 2;
+      const int gb0 = jc * NUB, gz0 = jc * NZB;
+      bool zwaited = false;
       // z-block zi: D2 slot -> +hb -> bf16 -> rows [r0, r0 + 16) of this segment in the z tile
       auto extract = [&](int zi) {
         const int r0 = (16 * zi < S - 16) ? 16 * zi : S - 16;
-        mbar_wait(d2full0 + 8 * dslot, dph);
+        const int gz = gz0 + zi, dslot = gz & 1;
+        mbar_wait(d2full0 + 8 * dslot, (gz >> 1) & 1);
         tc_fence_after();
         uint32_t v[16];
         asm volatile(
@@ -424,26 +447,45 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(d2empty0 + 8 * dslot);
-        if (++dslot == 2) { dslot = 0; dph ^= 1; }
-        if (zi == 0 && !(a.dbg & 16)) mbar_wait(BAR_ZEMPTY(zs), ((n / NZF) & 1) ^ 1);   // conv MMAs of this slot's previous chunk retired
+        if (!zwaited) {                              // conv MMAs of this z slot's previous chunk retired
+          if (!(a.dbg & 16)) mbar_wait(BAR_ZEMPTY(zs), ((n / NZF) & 1) ^ 1);
+          zwaited = true;
+        }
         uint8_t* zblk = zrow0 + r0 * 16;
+        if (a.dbg & 64) return;
 #pragma unroll
-        for (int r = 0; r < 16; r += 2) {
-          float z0 = __uint_as_float(v[r]) + hbf, z1 = __uint_as_float(v[r + 1]) + hbf;
+        for (int rr = 0; rr < 16; rr += 2) {
+          float z0 = __uint_as_float(v[rr]) + hbf, z1 = __uint_as_float(v[rr + 1]) + hbf;
           if (edge) {
-            const int tm_ = ts + r0 + r;
+            const int tm_ = ts + r0 + rr;
             if (tm_ < 0 || tm_ >= T) z0 = 0.f;                    // conv zero padding (utils.py:59)
             if (tm_ + 1 < 0 || tm_ + 1 >= T) z1 = 0.f;
           }
           __nv_bfloat162 o = __floats2bfloat162_rn(z0, z1);
-          *reinterpret_cast<__nv_bfloat16*>(zblk + r * 16) = o.x;
-          *reinterpret_cast<__nv_bfloat16*>(zblk + (r + 1) * 16) = o.y;
+          *reinterpret_cast<__nv_bfloat16*>(zblk + rr * 16) = o.x;
+          *reinterpret_cast<__nv_bfloat16*>(zblk + (rr + 1) * 16) = o.y;
+        }
+        if (edge) {
+          // rows within 6 samples of a sequence end see the replicate clamps of the two FIRs: exact scalar redo,
+          // by the thread that just stored the row (program order keeps the fix last)
+          const int nlo = T < 6 ? T : 6;
+#pragma unroll 1
+          for (int e = 0; e < 12; ++e) {
+            const int m = e < 6 ? e : T - 12 + e;
+            const bool valid = e < 6 ? (m < nlo) : (m >= nlo);
+            const int rho = m - ts;
+            if (valid && rho >= r0 && rho < r0 + 16) {
+              const float zf = fir_edge_z(xrow0, ts - 7, m, T, a2f, nhbf, a);
+              *reinterpret_cast<__nv_bfloat16*>(zrow0 + rho * 16) = __float2bfloat16_rn(zf);
+            }
+          }
         }
       };
-      int znext = 0;                                // next z-block to extract
+      int znext = (r + gz0) & (NR - 1);            // my next z-block of this chunk (global z-block parity)
 #pragma unroll 1
-      for (int bi = 0; bi < NUB; ++bi) {
-        mbar_wait(dfull0 + 8 * slot, sph);
+      for (int bi = (r + gb0) & (NR - 1); bi < NUB; bi += NR) {
+        const int gb = gb0 + bi, slot = gb & (NSLOT - 1);
+        mbar_wait(dfull0 + 8 * slot, (gb / NSLOT) & 1);
         tc_fence_after();
         uint32_t v[16];
         asm volatile(
@@ -453,6 +495,10 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
             : "r"(t_d1 + (uint32_t)(slot * 16)));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         uint32_t sw[8];
+        if (a.dbg & 32) {
+#pragma unroll
+          for (int p = 0; p < 8; ++p) sw[p] = v[p];
+        } else
 #pragma unroll
         for (int p = 0; p < 8; ++p) {
           // s' = u + nhb*cos(a2*u) on two consecutive up-sampled positions -> one fp16x2 TMEM column (even position low)
@@ -466,33 +512,25 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
                      ::"r"(t_s + (uint32_t)(bi * 8)), "r"(sw[0]), "r"(sw[1]), "r"(sw[2]), "r"(sw[3]), "r"(sw[4]), "r"(sw[5]),
                        "r"(sw[6]), "r"(sw[7]) : "memory");
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        // the arrival frees the D1 slot AND tells the issuer that this block's s columns are complete
+        // D1 slot free (up issuer) and this block's s columns complete (down issuer)
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(dempty0 + 8 * slot);
-        if (++slot == NSLOT) { slot = 0; sph ^= 1; }
-        // a z-block is issued when its last u-block (r0/8 + 2) completes; pick it up one block later
+        if (lane == 0) {
+          mbar_arrive(dempty0 + 8 * slot);
+          mbar_arrive(sfull0 + 8 * (gb & 3));
+        }
+        // a z-block is issued when its last u-block (r0/8 + 2) completes; pick mine up once that block is behind me
         if (znext < NZB) {
           const int r0n = (16 * znext < S - 16) ? 16 * znext : S - 16;
-          if ((r0n >> 3) + 2 < bi) { extract(znext); ++znext; }
+          if ((r0n >> 3) + 2 < bi) { extract(znext); znext += NR; }
         }
       }
-      while (znext < NZB) { extract(znext); ++znext; }
-      if (edge) {
-        // rows within 6 samples of a sequence end see the replicate clamps of the two FIRs: exact scalar redo
-        __syncwarp();
-        const int nlo = T < 6 ? T : 6;
-        const uint8_t* xrow0 = smem + FOFF_X + xs * X_SLOT + (q * 4 + g) * (XB * 16) + c8 * 2;
-#pragma unroll 1
-        for (int e = 0; e < 12; ++e) {
-          const int m = e < 6 ? e : T - 12 + e;
-          const bool valid = e < 6 ? (m < nlo) : (m >= nlo);
-          const int rho = m - ts;
-          if (valid && rho >= 0 && rho < S) {
-            const float zf = fir_edge_z(xrow0, ts - 7, m, T, a2f, nhbf, a);
-            *reinterpret_cast<__nv_bfloat16*>(zrow0 + rho * 16) = __float2bfloat16_rn(zf);
-          }
-        }
+      while (znext < NZB) { extract(znext); znext += NR; }
+      {
+        // every warp of the set waits for the chunk's LAST z-block: all down MMAs have then read their s columns,
+        // so the next chunk may overwrite them
+        const int gzl = gz0 + NZB - 1;
+        mbar_wait(d2full0 + 8 * (gzl & 1), (gzl >> 1) & 1);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // z stores -> async proxy (UMMA)
       __syncwarp();
@@ -502,7 +540,7 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
       }
     }
   } else if (warp < WARP_EPI) {
-    if (warp == WARP_X) {
+    if (warp == WARP_XW) {
       // ===================== x producer (TMA): 16 boxes (segment, channel group) per chunk =====================
       if (lane == 0) {
         TileCursor cur{prefix};
@@ -519,9 +557,8 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
             tma_load_4d(dst + j * (XB * 16), &tmx, 0, t0 - hc + (j >> 2) * S - 7, c * 4 + (j & 3), b, BAR_XFULL(xs));
         }
       }
-    } else if (warp == WARP_W) {
-      // ===================== weight producer (bulk copies) =====================
-      if (lane == 0) {
+      // ===================== weight producer (bulk copies), second lane of the same warp =====================
+      if (lane == 1) {
         int stage = 0, phase = 0;
         for (int it = 0; it < my_tiles; ++it) {
           const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wt);
@@ -537,47 +574,26 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
             }
         }
       }
-    } else if (warp >= WARP_FIR && warp < WARP_FIR + NSETS) {
-      // ===================== FIR MMA issuer of one set =====================
+    } else if (warp >= WARP_UP && warp < WARP_UP + NSETS) {
+      // ===================== up-FIR MMA issuer of one set: D1[slot] = X(block) * (UP_hi + UP_lo) =====================
       if (lane == 0) {
-        const int s = warp - WARP_FIR;
-        // up: A = x tile, MN-major SWIZZLE_NONE (LBO = stride between 8-row K groups, SBO = stride between 8-channel
-        // M groups), bf16; down: A = s in TMEM (fp16 pairs per column), B = fp16 taps
+        const int s = warp - WARP_UP;
+        // A = x tile, MN-major SWIZZLE_NONE (LBO = stride between 8-row K groups, SBO = stride between 8-channel M groups)
         const uint32_t idesc_up = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(16 >> 3) << 17) |
                                   ((uint32_t)(128 >> 4) << 24);
-        const uint32_t idesc_dn = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const u64 hiA = make_sdesc(0, 128, XB * 16);
         const u64 bhi = make_sdesc(s_base + FOFF_UPB, 16 * 16, 128), blo = make_sdesc(s_base + FOFF_UPB + 512, 16 * 16, 128);
-        const u64 bdn = make_sdesc(s_base + FOFF_DNB, 16 * 16, 128);
         const uint32_t dfull0 = BAR_DFULL(s * NSLOT_MAX), dempty0 = BAR_DEMPTY(s * NSLOT_MAX);
-        const uint32_t d2full0 = BAR_D2FULL(s * 2), d2empty0 = BAR_D2EMPTY(s * 2);
-        const uint32_t tset = tmem + TM_ACC + (uint32_t)(s * TM_SET);
-        const uint32_t t_d1 = tset, t_d2 = tset + 16 * NSLOT, t_s = tset + 16 * NSLOT + 32;
-        int slot = 0, ph = 0, dslot = 0, dph = 0;
-        // u-block cb of the current segment walk is complete (s columns written): issue the z-block it finishes
-        auto down_after = [&](int cb) {
-          int r0;
-          if (cb == NUB - 1) r0 = S - 16;
-          else if (cb >= 2 && !(cb & 1) && 8 * (cb - 2) < S - 16) r0 = 8 * (cb - 2);
-          else return;
-          mbar_wait(d2empty0 + 8 * dslot, dph ^ 1);
-          tc_fence_after();
-#pragma unroll
-          for (int ks = 0; ks < 3; ++ks)
-            umma_ts_f16(t_d2 + (uint32_t)(dslot * 16), t_s + (uint32_t)(r0 + ks * 8), bdn + (u64)(ks * 32), idesc_dn, ks > 0);
-          umma_commit(d2full0 + 8 * dslot);
-          if (++dslot == 2) { dslot = 0; dph ^= 1; }
-        };
-        int gb = 0;                                   // u-blocks issued so far by this set
+        const uint32_t t_d1 = tmem + TM_ACC + (uint32_t)(s * TM_SET);
+        int slot = 0, ph = 0;
         for (int n = s; n < total_chunks; n += NSETS) {
           const int xs = n & (NXF - 1);
           mbar_wait(BAR_XFULL(xs), (n / NXF) & 1);
           const uint32_t a0 = (s_base + FOFF_X + xs * X_SLOT) >> 4;
-#pragma unroll 1
-          for (int bi = 0; bi < NUB; ++bi, ++gb) {
-            mbar_wait(dempty0 + 8 * slot, ph ^ 1);    // u-block gb - NSLOT is complete (loaded, snaked, s written)
+#pragma unroll 2
+          for (int bi = 0; bi < NUB; ++bi) {
+            mbar_wait(dempty0 + 8 * slot, ph ^ 1);
             tc_fence_after();
-            if (gb >= NSLOT) down_after(bi >= NSLOT ? bi - NSLOT : bi - NSLOT + NUB);
             umma_bf16(t_d1 + (uint32_t)(slot * 16), hiA | (a0 + bi * 8), bhi, idesc_up, 0u);
             umma_bf16(t_d1 + (uint32_t)(slot * 16), hiA | (a0 + bi * 8), blo, idesc_up, 1u);
             umma_commit(dfull0 + 8 * slot);
@@ -585,13 +601,33 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
           }
           umma_commit(BAR_XEMPTY(xs));
         }
-        // drain: the last NSLOT u-blocks of the last chunk
-        const int tail = gb < NSLOT ? gb : NSLOT;
-        for (int i = 0; i < tail; ++i) {
-          mbar_wait(dempty0 + 8 * slot, ph ^ 1);
-          tc_fence_after();
-          down_after(NUB - tail + i);
-          if (++slot == NSLOT) { slot = 0; ph ^= 1; }
+      }
+    } else if (warp >= WARP_DN && warp < WARP_DN + NSETS) {
+      // ===================== down-FIR MMA issuer of one set: D2[slot] = S(z-block window, TMEM) * DN =====================
+      if (lane == 0) {
+        const int s = warp - WARP_DN;
+        const uint32_t idesc_dn = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // fp16 x fp16
+        const u64 bdn = make_sdesc(s_base + FOFF_DNB, 16 * 16, 128);
+        const uint32_t d2full0 = BAR_D2FULL(s * 2), d2empty0 = BAR_D2EMPTY(s * 2), sfull0 = BAR_SFULL(s * 4);
+        const uint32_t tset = tmem + TM_ACC + (uint32_t)(s * TM_SET);
+        const uint32_t t_d2 = tset + 16 * NSLOT, t_s = tset + 16 * NSLOT + 32;
+        int gb = 0, dslot = 0, dph = 0;
+        for (int n = s; n < total_chunks; n += NSETS) {
+#pragma unroll
+          for (int bi = 0; bi < NUB; ++bi, ++gb) {
+            // z-block finished by u-block bi (compile time): the last one, or the regular 16-row block ending here
+            constexpr int dummy = 0; (void)dummy;
+            const int r0 = (bi == NUB - 1) ? S - 16 : ((bi >= 2 && !(bi & 1) && 8 * (bi - 2) < S - 16) ? 8 * (bi - 2) : -1);
+            mbar_wait(sfull0 + 8 * (gb & 3), (gb >> 2) & 1);     // every phase is observed, in order
+            if (r0 < 0) continue;
+            mbar_wait(d2empty0 + 8 * dslot, dph ^ 1);
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < 3; ++ks)
+              umma_ts_f16(t_d2 + (uint32_t)(dslot * 16), t_s + (uint32_t)(r0 + ks * 8), bdn + (u64)(ks * 32), idesc_dn, ks > 0);
+            umma_commit(d2full0 + 8 * dslot);
+            if (++dslot == 2) { dslot = 0; dph ^= 1; }
+          }
         }
       }
     } else if (warp == WARP_CONV) {
