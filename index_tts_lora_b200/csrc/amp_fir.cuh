@@ -17,16 +17,18 @@
 // tcgen05.ld -> +hb -> bf16 -> z tile (the UMMA A operand of the conv).
 // Tile = 256 output rows x all C_out columns of one utterance; the 256 + 2*hc activated rows of a
 // 32-channel chunk are 4 time segments of S rows x 4 channel groups = 16 row groups = 128 TMEM lanes.
-// Segment q is handled by the warps with (warp & 3) == q; a set of 4 such warps owns a whole chunk and
-// NSETS chunks are in flight.  A segment is walked in NUB = S/8 + 1 u-blocks of 16 s samples (8 x rows);
-// z-block zi (16 rows from r0 = min(16 zi, S-16)) reads s columns [2 r0, 2 r0 + 48), complete after u-block r0/8 + 2.
+// Segment q is handled by the 4 warps with (warp & 3) == q, which split the columns.  Hand-overs between the
+// activation warps and the MMA issuers cost ~1-2 k cycles per round trip, so the granularity is a HALF chunk:
+// a segment's NUB = S/8 + 1 u-blocks of 16 s samples are issued as two batches into two D1 buffers, and the
+// z-blocks (16 rows from r0 = min(16 zi, S-16), reading s columns [2 r0, 2 r0 + 48)) as two batches into two D2
+// buffers; the second batch of a chunk is picked up while the next chunk's first half is in flight.
 //
-//   warps 0-15  activation sets     (2 sets x 2 alternating warps x 4 TMEM lane quarters)
+//   warps 0-15  activation          tcgen05.ld D1 -> snake -> fp16 -> tcgen05.st s;  tcgen05.ld D2 -> +hb -> bf16 z tile
 //   warp 16     lane 0: TMA producer, 16 boxes {8 ch, 96 rows} per chunk -> x ring; lane 1: weight producer (as k_amp_tc)
 //   warp 17     conv MMA issuer     (as k_amp_tc) on the z ring
-//   warps 18,19 up-FIR MMA issuers  one per set: two MMAs per u-block as D1 slots free up
-//   warps 20,21 down-FIR issuers    one per set: three MMAs per z-block as its s columns complete
-//   warps 22-25 epilogue            lean conv-mode epilogue
+//   warp 18     up-FIR MMA issuer   two MMAs (hi, lo taps) per u-block, one commit per half chunk
+//   warp 19     down-FIR MMA issuer three TS MMAs per z-block, one commit per half chunk
+//   warps 20-23 epilogue            lean conv-mode epilogue
 // Sequence edges (replicate clamps, activations.py / filter.py) are re-evaluated exactly for the <= 12
 // affected rows per utterance by a scalar path; rows outside [0, T) are the conv's zero padding.
 #pragma once
@@ -36,27 +38,24 @@ namespace bvg {
 namespace fir {
 using namespace tc;
 
-constexpr int NSETS = 2;                 // chunks in flight
-constexpr int NR = 2;                    // warps per (set, TMEM lane quarter), alternating blocks
-constexpr int NW_ACT = 4 * NR * NSETS;   // 16
-constexpr int WARP_XW = NW_ACT, WARP_CONV = NW_ACT + 1, WARP_UP = NW_ACT + 2, WARP_DN = WARP_UP + NSETS, WARP_EPI = WARP_DN + NSETS;
-constexpr int NTHREADS_F = (WARP_EPI + 4) * 32;      // 832
+constexpr int NW_ACT = 16;               // 4 TMEM lane quarters (= time segments) x 4 warps sharing a quarter's columns
+constexpr int WARP_XW = NW_ACT, WARP_CONV = NW_ACT + 1, WARP_UP = NW_ACT + 2, WARP_DN = NW_ACT + 3, WARP_EPI = NW_ACT + 4;
+constexpr int NTHREADS_F = (WARP_EPI + 4) * 32;      // 768
 constexpr int NXF = 4, NZF = 4;          // x / z ring depths
 constexpr int XB = 96;                   // TMA box rows per (segment, channel group): S + 16 <= 96
 constexpr int X_SLOT = 16 * XB * 16;     // 24576
 constexpr int ZRF = 322;                 // z rows per channel group: >= 4*80, = 2 (mod 8) -> conflict-free 2-byte stores
 constexpr int Z_SLOT = 4 * ZRF * 16;     // 20608
 constexpr int W_STAGES_F = 2;
-constexpr int NSLOT_MAX = 4;
-constexpr int MAX_NTILE_F = 96;
-// TMEM columns: [0, ACC) conv accumulators, then per set: NSLOT D1 slots of 16 | 2 D2 slots of 16 | 96 columns of s
-__host__ __device__ constexpr int tm_per_set(int nslot) { return 16 * nslot + 32 + 96; }
-__host__ __device__ constexpr int tm_acc(int nslot) { return 512 - NSETS * tm_per_set(nslot); }
+constexpr int MAX_NTILE_F = 64;
+// TMEM columns: [0,128) conv accumulators | [128,320) two D1 half-chunk buffers of 96 | [320,416) s (fp16 pairs) |
+// [416,512) two D2 half-chunk buffers of 48
+constexpr int TM_ACC = 128, TM_D1 = 128, TM_S = 320, TM_D2 = 416;
 
 constexpr int FOFF_BIAS = 0;
 constexpr int FOFF_PREFIX = FOFF_BIAS + 2 * 256 * 4;
 constexpr int FOFF_BAR = FOFF_PREFIX + (MAX_B + 8) * 4;
-constexpr int F_NUM_BARS = 2 * NXF + 2 * NSLOT_MAX * NSETS + 4 * NSETS + 4 * NSETS + 2 * NZF + 2 * W_STAGES_F + 4;
+constexpr int F_NUM_BARS = 2 * NXF + 10 + 2 * NZF + 2 * W_STAGES_F + 4;
 constexpr int FOFF_TMEM = FOFF_BAR + F_NUM_BARS * 8;
 constexpr int FOFF_UPB = (FOFF_TMEM + 16 + 127) / 128 * 128;   // 2 x [2][16][8] bf16 up taps (hi, lo), then [6][16][8] fp16 down taps
 constexpr int FOFF_DNB = FOFF_UPB + 1024;
@@ -295,14 +294,15 @@ __device__ __forceinline__ uint32_t f2_to_h2_sat(float lo, float hi) {     // {h
   return r;
 }
 
-template <int NUB, int NSLOT>
+template <int NUB>
 __global__ void __launch_bounds__(NTHREADS_F, 1)
 k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int S = 8 * (NUB - 1);           // z rows per segment
   constexpr int NZB = (S + 15) / 16;         // z-blocks per segment (the last one may overlap its predecessor)
-  constexpr int TM_ACC = tm_acc(NSLOT), TM_SET = tm_per_set(NSLOT);
-  static_assert(S + 16 <= XB && 4 * S <= ZRF && 2 * NUB * 8 <= 192, "segment geometry");
+  constexpr int NB0 = (NUB + 1) / 2, NB1 = NUB - NB0;   // u-blocks per half chunk
+  constexpr int NZ0 = 2, NZ1 = NZB - 2;                 // z-blocks per half chunk: windows [2 r0, 2 r0 + 48) inside the half's s
+  static_assert(S + 16 <= XB && 4 * S <= ZRF && NB0 * 16 <= 96 && NZ1 * 16 <= 48 && 48 <= 16 * NB0 && NZ1 >= 1, "segment geometry");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tile = a.n_tile;
 
@@ -310,12 +310,12 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
   const uint32_t bar0 = s_base + FOFF_BAR;
   auto BAR_XFULL = [&](int i) { return bar0 + 8 * i; };
   auto BAR_XEMPTY = [&](int i) { return bar0 + 8 * (NXF + i); };
-  auto BAR_DFULL = [&](int i) { return bar0 + 8 * (2 * NXF + i); };                              // i = set*NSLOT_MAX + slot
-  auto BAR_DEMPTY = [&](int i) { return bar0 + 8 * (2 * NXF + NSLOT_MAX * NSETS + i); };
-  auto BAR_D2FULL = [&](int i) { return bar0 + 8 * (2 * NXF + 2 * NSLOT_MAX * NSETS + i); };      // i = set*2 + slot
-  auto BAR_D2EMPTY = [&](int i) { return bar0 + 8 * (2 * NXF + 2 * NSLOT_MAX * NSETS + 2 * NSETS + i); };
-  auto BAR_SFULL = [&](int i) { return bar0 + 8 * (2 * NXF + 2 * NSLOT_MAX * NSETS + 4 * NSETS + i); };        // i = set*4 + (block & 3)
-  constexpr int BZ = 2 * NXF + 2 * NSLOT_MAX * NSETS + 4 * NSETS + 4 * NSETS;
+  auto BAR_DFULL = [&](int h) { return bar0 + 8 * (2 * NXF + h); };           // h = half
+  auto BAR_DEMPTY = [&](int h) { return bar0 + 8 * (2 * NXF + 2 + h); };
+  auto BAR_SFULL = [&](int h) { return bar0 + 8 * (2 * NXF + 4 + h); };
+  auto BAR_D2FULL = [&](int h) { return bar0 + 8 * (2 * NXF + 6 + h); };
+  auto BAR_D2EMPTY = [&](int h) { return bar0 + 8 * (2 * NXF + 8 + h); };
+  constexpr int BZ = 2 * NXF + 10;
   auto BAR_ZFULL = [&](int i) { return bar0 + 8 * (BZ + i); };
   auto BAR_ZEMPTY = [&](int i) { return bar0 + 8 * (BZ + NZF + i); };
   auto BAR_WFULL = [&](int i) { return bar0 + 8 * (BZ + 2 * NZF + i); };
@@ -354,11 +354,12 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
     if (lane == 0) prefix[0] = 0;
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < NXF; ++i) { mbar_init(BAR_XFULL(i), 1); mbar_init(BAR_XEMPTY(i), 1 + 4 * NR); }
-    for (int i = 0; i < NSLOT_MAX * NSETS; ++i) { mbar_init(BAR_DFULL(i), 1); mbar_init(BAR_DEMPTY(i), 4); }
-    for (int i = 0; i < 2 * NSETS; ++i) { mbar_init(BAR_D2FULL(i), 1); mbar_init(BAR_D2EMPTY(i), 4); }
-    for (int i = 0; i < 4 * NSETS; ++i) mbar_init(BAR_SFULL(i), 4);
-    for (int i = 0; i < NZF; ++i) { mbar_init(BAR_ZFULL(i), 4 * NR); mbar_init(BAR_ZEMPTY(i), 1); }
+    for (int i = 0; i < NXF; ++i) { mbar_init(BAR_XFULL(i), 1); mbar_init(BAR_XEMPTY(i), 1 + NW_ACT); }
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(BAR_DFULL(h), 1); mbar_init(BAR_DEMPTY(h), NW_ACT); mbar_init(BAR_SFULL(h), NW_ACT);
+      mbar_init(BAR_D2FULL(h), 1); mbar_init(BAR_D2EMPTY(h), NW_ACT);
+    }
+    for (int i = 0; i < NZF; ++i) { mbar_init(BAR_ZFULL(i), NW_ACT); mbar_init(BAR_ZEMPTY(i), 1); }
     for (int i = 0; i < W_STAGES_F; ++i) { mbar_init(BAR_WFULL(i), 1); mbar_init(BAR_WEMPTY(i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(BAR_ACCFULL(i), 1); mbar_init(BAR_ACCEMPTY(i), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -404,142 +405,151 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
   const int total_chunks = my_tiles * NCH;
 
   if (warp < NW_ACT) {
-    // ===================== activation sets =====================
-    // warp = (set, r, q): q = TMEM lane quarter = time segment, r = one of the NR warps that share the quarter and
-    // take the set's u-blocks / z-blocks alternately (global block parity), so slots and phases follow from the
-    // block counters alone and no state is carried between blocks.
-    const int set = warp / (4 * NR), r = (warp >> 2) % NR, q = warp & 3, g = lane >> 3, c8 = lane & 7;
-    const uint32_t tset = tmem + ((uint32_t)(q * 32) << 16) + TM_ACC + (uint32_t)(set * TM_SET);
-    const uint32_t t_d1 = tset, t_d2 = tset + 16 * NSLOT, t_s = tset + 16 * NSLOT + 32;
-    const uint32_t dfull0 = BAR_DFULL(set * NSLOT_MAX), dempty0 = BAR_DEMPTY(set * NSLOT_MAX);
-    const uint32_t d2full0 = BAR_D2FULL(set * 2), d2empty0 = BAR_D2EMPTY(set * 2), sfull0 = BAR_SFULL(set * 4);
+    // ===================== activation warps =====================
+    // warp = (r, q): q = TMEM lane quarter = time segment, r = which quarter of a half chunk's columns
+    const int q = warp & 3, r = warp >> 2, g = lane >> 3, c8 = lane & 7;
+    const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
+    struct Ctx {
+      uint8_t* zrow0; const uint8_t* xrow0;
+      int ts, T, zs, xs, n;
+      float a2f, nhbf;
+      bool edge;
+    };
+    // one stored z value: row rho of the segment; sequence-edge rows are re-evaluated exactly (scalar), rows outside
+    // [0, T) are the conv's zero padding (utils.py:59)
+    auto put_z = [&](const Ctx& cx, int rho, float zv) {
+      if (cx.edge) {
+        const int m = cx.ts + rho;
+        if (m < 0 || m >= cx.T) zv = 0.f;
+        else if (m < 6 || m >= cx.T - 6) zv = fir_edge_z(cx.xrow0, cx.ts - 7, m, cx.T, cx.a2f, cx.nhbf, a);
+      }
+      *reinterpret_cast<__nv_bfloat16*>(cx.zrow0 + rho * 16) = __float2bfloat16_rn(zv);
+    };
+    // D2 buffer of half h (z-blocks of that half, 16 columns each): my quarter of its columns -> +hb -> z tile
+    auto extract = [&](const Ctx& cx, int h) {
+      mbar_wait(BAR_D2FULL(h), cx.n & 1);
+      tc_fence_after();
+      uint32_t v[12];
+      const int c0 = h == 0 ? 8 * r : 4 * NZ1 * r;                 // first of my columns in the buffer
+      const int nc = h == 0 ? 8 : 4 * NZ1;                         // 8 | 4, 8 or 12 columns
+      const uint32_t ta = tq + TM_D2 + (uint32_t)(h * 48 + c0);
+      if (nc >= 8)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(ta));
+      if (nc == 4)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(ta));
+      if (nc == 12)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]) : "r"(ta + 8));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR_D2EMPTY(h));
+      if (h == 0 && !(a.dbg & 16)) mbar_wait(BAR_ZEMPTY(cx.zs), ((cx.n / NZF) & 1) ^ 1);   // conv MMAs of this z slot's previous chunk retired
+      if (a.dbg & 64) return;
+      const float hbf = -cx.nhbf;
+#pragma unroll
+      for (int j = 0; j < 12; ++j) {
+        if (j >= nc) break;
+        const int c = c0 + j;                                       // column in the half's buffer
+        const int zb = (h == 0 ? 0 : NZ0) + (c >> 4);               // z-block of the segment
+        const int r0 = (16 * zb < S - 16) ? 16 * zb : S - 16;
+        put_z(cx, r0 + (c & 15), __uint_as_float(v[j]) + hbf);
+      }
+    };
+    // D1 buffer of half h: my quarter of its columns -> snake -> fp16 pairs (returned in sw[]), D1 buffer released
+    auto load_snake = [&](int h, int ph, u64 a2p, u64 nhbp, uint32_t* sw) {
+      mbar_wait(BAR_DFULL(h), ph);
+      tc_fence_after();
+      const int cw = (h == 0 ? NB0 : NB1) * 4;                      // my columns of the half: 20 or 24
+      const uint32_t ta = tq + TM_D1 + (uint32_t)(h * 96 + r * cw);
+      uint32_t v[24];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+          : "r"(ta));
+      if (cw == 24)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23])
+                     : "r"(ta + 16));
+      else
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]) : "r"(ta + 16));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR_DEMPTY(h));
+#pragma unroll
+      for (int p = 0; p < 12; ++p) {
+        if (2 * p >= cw) break;
+        if (a.dbg & 32) { sw[p] = v[p]; continue; }
+        // s' = u + nhb*cos(a2*u) on two consecutive up-sampled positions -> one fp16x2 TMEM column (even position low)
+        const u64 u = pk(__uint_as_float(v[2 * p]), __uint_as_float(v[2 * p + 1]));
+        float t0f, t1f, s0, s1;
+        upk(mul2(a2p, u), t0f, t1f);
+        upk(fma2(nhbp, pk(__cosf(t0f), __cosf(t1f)), u), s0, s1);
+        sw[p] = f2_to_h2_sat(s0, s1);
+      }
+    };
+    auto store_s = [&](int h, const uint32_t* sw) {
+      const int cw2 = (h == 0 ? NB0 : NB1) * 2;                     // my s columns (fp16 pairs): 10 or 12
+      const uint32_t ta = tq + TM_S + (uint32_t)((h == 0 ? 0 : NB0 * 8) + r * cw2);
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                   ::"r"(ta), "r"(sw[0]), "r"(sw[1]), "r"(sw[2]), "r"(sw[3]), "r"(sw[4]), "r"(sw[5]), "r"(sw[6]), "r"(sw[7]) : "memory");
+      if (cw2 == 12)
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
+                     ::"r"(ta + 8), "r"(sw[8]), "r"(sw[9]), "r"(sw[10]), "r"(sw[11]) : "memory");
+      else
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(ta + 8), "r"(sw[8]), "r"(sw[9]) : "memory");
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR_SFULL(h));
+    };
+    auto finish = [&](const Ctx& cx) {                              // second half of a chunk, then hand the z / x slots over
+      extract(cx, 1);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // z stores -> async proxy (UMMA)
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(BAR_ZFULL(cx.zs));
+        mbar_arrive(BAR_XEMPTY(cx.xs));
+      }
+    };
     TileCursor cur{prefix};
-    int jc = 0;                                    // chunks of this set processed so far
-    for (int n = set; n < total_chunks; n += NSETS, ++jc) {
+    Ctx prev;
+    prev.n = -1;
+    for (int n = 0; n < total_chunks; ++n) {
       const int it = n / NCH, c = n - it * NCH;
       int b, t0, nt;
       cur.locate((int)blockIdx.x + it * (int)gridDim.x, 1, b, t0, nt);
-      const int T = a.lengths ? a.lengths[b] * a.rate : a.Tmax;
-      const int ts = t0 - hc + q * S;              // time of this segment's z row 0
+      Ctx cx;
+      cx.n = n;
+      cx.T = a.lengths ? a.lengths[b] * a.rate : a.Tmax;
+      cx.ts = t0 - hc + q * S;                     // time of this segment's z row 0
       const int ch = c * KC + g * 8 + c8;
-      const float a2f = __ldg(a.a2 + ch), nhbf = __ldg(a.nhb + ch);
-      const u64 a2p = pk(a2f, a2f), nhbp = pk(nhbf, nhbf);
-      const float hbf = -nhbf;
-      const bool edge = (ts - 8 < 0) || (ts + S + 8 > T);          // warp-uniform
-      const int xs = n & (NXF - 1), zs = n & (NZF - 1);
-      uint8_t* zrow0 = smem + FOFF_Z + zs * Z_SLOT + g * (ZRF * 16) + (q * S) * 16 + c8 * 2;
-      const uint8_t* xrow0 = smem + FOFF_X + xs * X_SLOT + (q * 4 + g) * (XB * 16) + c8 * 2;
-      const int gb0 = jc * NUB, gz0 = jc * NZB;
-      bool zwaited = false;
-      // z-block zi: D2 slot -> +hb -> bf16 -> rows [r0, r0 + 16) of this segment in the z tile
-      auto extract = [&](int zi) {
-        const int r0 = (16 * zi < S - 16) ? 16 * zi : S - 16;
-        const int gz = gz0 + zi, dslot = gz & 1;
-        mbar_wait(d2full0 + 8 * dslot, (gz >> 1) & 1);
-        tc_fence_after();
-        uint32_t v[16];
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-            : "r"(t_d2 + (uint32_t)(dslot * 16)));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(d2empty0 + 8 * dslot);
-        if (!zwaited) {                              // conv MMAs of this z slot's previous chunk retired
-          if (!(a.dbg & 16)) mbar_wait(BAR_ZEMPTY(zs), ((n / NZF) & 1) ^ 1);
-          zwaited = true;
-        }
-        uint8_t* zblk = zrow0 + r0 * 16;
-        if (a.dbg & 64) return;
-#pragma unroll
-        for (int rr = 0; rr < 16; rr += 2) {
-          float z0 = __uint_as_float(v[rr]) + hbf, z1 = __uint_as_float(v[rr + 1]) + hbf;
-          if (edge) {
-            const int tm_ = ts + r0 + rr;
-            if (tm_ < 0 || tm_ >= T) z0 = 0.f;                    // conv zero padding (utils.py:59)
-            if (tm_ + 1 < 0 || tm_ + 1 >= T) z1 = 0.f;
-          }
-          __nv_bfloat162 o = __floats2bfloat162_rn(z0, z1);
-          *reinterpret_cast<__nv_bfloat16*>(zblk + rr * 16) = o.x;
-          *reinterpret_cast<__nv_bfloat16*>(zblk + (rr + 1) * 16) = o.y;
-        }
-        if (edge) {
-          // rows within 6 samples of a sequence end see the replicate clamps of the two FIRs: exact scalar redo,
-          // by the thread that just stored the row (program order keeps the fix last)
-          const int nlo = T < 6 ? T : 6;
-#pragma unroll 1
-          for (int e = 0; e < 12; ++e) {
-            const int m = e < 6 ? e : T - 12 + e;
-            const bool valid = e < 6 ? (m < nlo) : (m >= nlo);
-            const int rho = m - ts;
-            if (valid && rho >= r0 && rho < r0 + 16) {
-              const float zf = fir_edge_z(xrow0, ts - 7, m, T, a2f, nhbf, a);
-              *reinterpret_cast<__nv_bfloat16*>(zrow0 + rho * 16) = __float2bfloat16_rn(zf);
-            }
-          }
-        }
-      };
-      int znext = (r + gz0) & (NR - 1);            // my next z-block of this chunk (global z-block parity)
-#pragma unroll 1
-      for (int bi = (r + gb0) & (NR - 1); bi < NUB; bi += NR) {
-        const int gb = gb0 + bi, slot = gb & (NSLOT - 1);
-        mbar_wait(dfull0 + 8 * slot, (gb / NSLOT) & 1);
-        tc_fence_after();
-        uint32_t v[16];
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-            : "r"(t_d1 + (uint32_t)(slot * 16)));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        uint32_t sw[8];
-        if (a.dbg & 32) {
-#pragma unroll
-          for (int p = 0; p < 8; ++p) sw[p] = v[p];
-        } else
-#pragma unroll
-        for (int p = 0; p < 8; ++p) {
-          // s' = u + nhb*cos(a2*u) on two consecutive up-sampled positions -> one fp16x2 TMEM column (even position low)
-          const u64 u = pk(__uint_as_float(v[2 * p]), __uint_as_float(v[2 * p + 1]));
-          float t0f, t1f, s0, s1;
-          upk(mul2(a2p, u), t0f, t1f);
-          upk(fma2(nhbp, pk(__cosf(t0f), __cosf(t1f)), u), s0, s1);
-          sw[p] = f2_to_h2_sat(s0, s1);
-        }
-        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                     ::"r"(t_s + (uint32_t)(bi * 8)), "r"(sw[0]), "r"(sw[1]), "r"(sw[2]), "r"(sw[3]), "r"(sw[4]), "r"(sw[5]),
-                       "r"(sw[6]), "r"(sw[7]) : "memory");
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        // D1 slot free (up issuer) and this block's s columns complete (down issuer)
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(dempty0 + 8 * slot);
-          mbar_arrive(sfull0 + 8 * (gb & 3));
-        }
-        // a z-block is issued when its last u-block (r0/8 + 2) completes; pick mine up once that block is behind me
-        if (znext < NZB) {
-          const int r0n = (16 * znext < S - 16) ? 16 * znext : S - 16;
-          if ((r0n >> 3) + 2 < bi) { extract(znext); znext += NR; }
-        }
-      }
-      while (znext < NZB) { extract(znext); znext += NR; }
-      {
-        // every warp of the set waits for the chunk's LAST z-block: all down MMAs have then read their s columns,
-        // so the next chunk may overwrite them
-        const int gzl = gz0 + NZB - 1;
-        mbar_wait(d2full0 + 8 * (gzl & 1), (gzl >> 1) & 1);
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // z stores -> async proxy (UMMA)
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(BAR_ZFULL(zs));
-        mbar_arrive(BAR_XEMPTY(xs));
-      }
+      cx.a2f = __ldg(a.a2 + ch);
+      cx.nhbf = __ldg(a.nhb + ch);
+      const u64 a2p = pk(cx.a2f, cx.a2f), nhbp = pk(cx.nhbf, cx.nhbf);
+      cx.edge = (cx.ts - 8 < 0) || (cx.ts + S + 8 > cx.T);          // warp-uniform
+      cx.xs = n & (NXF - 1);
+      cx.zs = n & (NZF - 1);
+      cx.zrow0 = smem + FOFF_Z + cx.zs * Z_SLOT + g * (ZRF * 16) + (q * S) * 16 + c8 * 2;
+      cx.xrow0 = smem + FOFF_X + cx.xs * X_SLOT + (q * 4 + g) * (XB * 16) + c8 * 2;
+      uint32_t sw[12];
+      load_snake(0, n & 1, a2p, nhbp, sw);
+      // the previous chunk's second batch of z-blocks: its MMAs are done reading s before this chunk overwrites it
+      if (prev.n >= 0) finish(prev);
+      store_s(0, sw);
+      load_snake(1, n & 1, a2p, nhbp, sw);
+      store_s(1, sw);
+      extract(cx, 0);
+      prev = cx;
     }
+    if (prev.n >= 0) finish(prev);
   } else if (warp < WARP_EPI) {
+    reg_dec<40>();
     if (warp == WARP_XW) {
       // ===================== x producer (TMA): 16 boxes (segment, channel group) per chunk =====================
       if (lane == 0) {
@@ -552,9 +562,17 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
           mbar_wait_relaxed(BAR_XEMPTY(xs), ((n / NXF) & 1) ^ 1, 200);
           mbar_expect_tx(BAR_XFULL(xs), X_SLOT);
           const uint32_t dst = s_base + FOFF_X + xs * X_SLOT;
+          // A box is XB consecutive 16-byte rows of one (utterance, channel group): contiguous in HBM.  Interior boxes
+          // are single 1-D bulk copies (the tensor path walks a box row by row, ~1 row / clk); boxes that leave
+          // [0, Tmax) or name a channel group beyond the tensor keep the tensor path for its zero fill.
 #pragma unroll 1
-          for (int j = 0; j < 16; ++j)
-            tma_load_4d(dst + j * (XB * 16), &tmx, 0, t0 - hc + (j >> 2) * S - 7, c * 4 + (j & 3), b, BAR_XFULL(xs));
+          for (int j = 0; j < 16; ++j) {
+            const int ts = t0 - hc + (j >> 2) * S - 7, grp = c * 4 + (j & 3);
+            if (ts >= 0 && ts + XB <= a.Tmax && grp < a.xgroups && !(a.dbg & 128))
+              bulk_load(dst + j * (XB * 16), a.xin + (((size_t)b * a.xgroups + grp) * a.Tmax + ts) * 8, XB * 16, BAR_XFULL(xs));
+            else
+              tma_load_4d(dst + j * (XB * 16), &tmx, 0, ts, grp, b, BAR_XFULL(xs));
+          }
         }
       }
       // ===================== weight producer (bulk copies), second lane of the same warp =====================
@@ -574,59 +592,57 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
             }
         }
       }
-    } else if (warp >= WARP_UP && warp < WARP_UP + NSETS) {
-      // ===================== up-FIR MMA issuer of one set: D1[slot] = X(block) * (UP_hi + UP_lo) =====================
+    } else if (warp == WARP_UP) {
+      // ===================== up-FIR MMA issuer: D1[half] = X(blocks of the half) * (UP_hi + UP_lo) =====================
       if (lane == 0) {
-        const int s = warp - WARP_UP;
         // A = x tile, MN-major SWIZZLE_NONE (LBO = stride between 8-row K groups, SBO = stride between 8-channel M groups)
         const uint32_t idesc_up = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(16 >> 3) << 17) |
                                   ((uint32_t)(128 >> 4) << 24);
         const u64 hiA = make_sdesc(0, 128, XB * 16);
         const u64 bhi = make_sdesc(s_base + FOFF_UPB, 16 * 16, 128), blo = make_sdesc(s_base + FOFF_UPB + 512, 16 * 16, 128);
-        const uint32_t dfull0 = BAR_DFULL(s * NSLOT_MAX), dempty0 = BAR_DEMPTY(s * NSLOT_MAX);
-        const uint32_t t_d1 = tmem + TM_ACC + (uint32_t)(s * TM_SET);
-        int slot = 0, ph = 0;
-        for (int n = s; n < total_chunks; n += NSETS) {
+        for (int n = 0; n < total_chunks; ++n) {
           const int xs = n & (NXF - 1);
           mbar_wait(BAR_XFULL(xs), (n / NXF) & 1);
           const uint32_t a0 = (s_base + FOFF_X + xs * X_SLOT) >> 4;
-#pragma unroll 2
-          for (int bi = 0; bi < NUB; ++bi) {
-            mbar_wait(dempty0 + 8 * slot, ph ^ 1);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(BAR_DEMPTY(h), (n & 1) ^ 1);
             tc_fence_after();
-            umma_bf16(t_d1 + (uint32_t)(slot * 16), hiA | (a0 + bi * 8), bhi, idesc_up, 0u);
-            umma_bf16(t_d1 + (uint32_t)(slot * 16), hiA | (a0 + bi * 8), blo, idesc_up, 1u);
-            umma_commit(dfull0 + 8 * slot);
-            if (++slot == NSLOT) { slot = 0; ph ^= 1; }
+            const int b0 = h == 0 ? 0 : NB0, nb = h == 0 ? NB0 : NB1;
+#pragma unroll
+            for (int i = 0; i < nb; ++i) {
+              if ((a.dbg & 256) && i > 0) break;          // timing experiments only
+              const uint32_t td = tmem + TM_D1 + (uint32_t)(h * 96 + i * 16);
+              umma_bf16(td, hiA | (a0 + (b0 + i) * 8), bhi, idesc_up, 0u);
+              umma_bf16(td, hiA | (a0 + (b0 + i) * 8), blo, idesc_up, 1u);
+            }
+            umma_commit(BAR_DFULL(h));
           }
           umma_commit(BAR_XEMPTY(xs));
         }
       }
-    } else if (warp >= WARP_DN && warp < WARP_DN + NSETS) {
-      // ===================== down-FIR MMA issuer of one set: D2[slot] = S(z-block window, TMEM) * DN =====================
+    } else if (warp == WARP_DN) {
+      // ===================== down-FIR MMA issuer: D2[half] = S(z-block windows, TMEM) * DN =====================
       if (lane == 0) {
-        const int s = warp - WARP_DN;
         const uint32_t idesc_dn = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // fp16 x fp16
         const u64 bdn = make_sdesc(s_base + FOFF_DNB, 16 * 16, 128);
-        const uint32_t d2full0 = BAR_D2FULL(s * 2), d2empty0 = BAR_D2EMPTY(s * 2), sfull0 = BAR_SFULL(s * 4);
-        const uint32_t tset = tmem + TM_ACC + (uint32_t)(s * TM_SET);
-        const uint32_t t_d2 = tset + 16 * NSLOT, t_s = tset + 16 * NSLOT + 32;
-        int gb = 0, dslot = 0, dph = 0;
-        for (int n = s; n < total_chunks; n += NSETS) {
+        for (int n = 0; n < total_chunks; ++n) {
 #pragma unroll
-          for (int bi = 0; bi < NUB; ++bi, ++gb) {
-            // z-block finished by u-block bi (compile time): the last one, or the regular 16-row block ending here
-            constexpr int dummy = 0; (void)dummy;
-            const int r0 = (bi == NUB - 1) ? S - 16 : ((bi >= 2 && !(bi & 1) && 8 * (bi - 2) < S - 16) ? 8 * (bi - 2) : -1);
-            mbar_wait(sfull0 + 8 * (gb & 3), (gb >> 2) & 1);     // every phase is observed, in order
-            if (r0 < 0) continue;
-            mbar_wait(d2empty0 + 8 * dslot, dph ^ 1);
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(BAR_SFULL(h), n & 1);
+            mbar_wait(BAR_D2EMPTY(h), (n & 1) ^ 1);
             tc_fence_after();
+            const int z0 = h == 0 ? 0 : NZ0, nz = h == 0 ? NZ0 : NZ1;
 #pragma unroll
-            for (int ks = 0; ks < 3; ++ks)
-              umma_ts_f16(t_d2 + (uint32_t)(dslot * 16), t_s + (uint32_t)(r0 + ks * 8), bdn + (u64)(ks * 32), idesc_dn, ks > 0);
-            umma_commit(d2full0 + 8 * dslot);
-            if (++dslot == 2) { dslot = 0; dph ^= 1; }
+            for (int i = 0; i < nz; ++i) {
+              if ((a.dbg & 512) && i > 0) break;          // timing experiments only
+              const int r0 = (16 * (z0 + i) < S - 16) ? 16 * (z0 + i) : S - 16;
+#pragma unroll
+              for (int ks = 0; ks < 3; ++ks)
+                umma_ts_f16(tmem + TM_D2 + (uint32_t)(h * 48 + i * 16), tmem + TM_S + (uint32_t)(r0 + ks * 8), bdn + (u64)(ks * 32),
+                            idesc_dn, ks > 0);
+            }
+            umma_commit(BAR_D2FULL(h));
           }
         }
       }
@@ -676,6 +692,7 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
     }
   } else {
     // ===================== epilogue warps =====================
+    reg_inc<120>();
     epilogue_fir(a, bias_s, prefix, BAR_ACCFULL(0), BAR_ACCEMPTY(0), tmem, nacc, total_tiles, warp & 3, lane,
                  threadIdx.x - WARP_EPI * 32);
   }

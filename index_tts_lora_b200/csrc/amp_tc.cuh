@@ -70,6 +70,8 @@ struct TcArgs {
   float div;
   int Cin, Cout, K, dil, n_tile, n_tiles, taps_per_stage;
   int nx, nz, wst;             // ring depths: x buffers (2..3), z buffers (2..4), weight stages (<= 8)
+  const __nv_bfloat16* xin;    // k_amp_fir: the blocked input buffer itself (interior boxes are plain 1-D bulk copies)
+  int xgroups;                 // channel groups of xin
   int dbg;                     // timing experiments only (BVG_DBG env): 1 = 1 of 4 MMAs per tap, 2 = 16-byte weight copies
   int st_lo, st_hi;            // conv mode: only rows in [st_lo, st_hi) are stored (time-split shards keep
                                // their hands off the halo rows that the neighbouring GPUs write)

@@ -325,9 +325,9 @@ static int launch_inst(const CUtensorMap& map, const TcArgs& a, dim3 grid, cudaS
   return 0;
 }
 
-template <int NUB, int NSLOT>
+template <int NUB>
 static int launch_fir_inst(const CUtensorMap& map, const TcArgs& a, dim3 grid, cudaStream_t st) {
-  auto kern = fir::k_amp_fir<NUB, NSLOT>;
+  auto kern = fir::k_amp_fir<NUB>;
   static bool attr = false;
   if (!attr) {
     BVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fir::F_SMEM));
@@ -340,7 +340,7 @@ static int launch_fir_inst(const CUtensorMap& map, const TcArgs& a, dim3 grid, c
 
 // narrow activated layers take k_amp_fir (up-sampling FIR on the tensor cores); BVG_FIR_MAX_C=0 disables it
 static int fir_max_c() {
-  static const int v = [] { const char* e = getenv("BVG_FIR_MAX_C"); return e ? atoi(e) : 96; }();
+  static const int v = [] { const char* e = getenv("BVG_FIR_MAX_C"); return e ? atoi(e) : 64; }();
   return v;
 }
 
@@ -395,11 +395,9 @@ static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, cons
     else rc = make_map(q.x, cw.Cin, q.Tstride, q.B, &tmp, 0, fir::XB);
     if (rc) return rc;
     a.wst = fir::W_STAGES_F;
-    // D1 slots per set: 4 when the conv accumulators leave room in TMEM (2 * n_tile <= 128 columns), else 2
-    if (2 * L.n_tile <= fir::tm_acc(4))
-      rc = (hc <= 16) ? launch_fir_inst<10, 4>(*fm, a, grid, st) : launch_fir_inst<11, 4>(*fm, a, grid, st);
-    else
-      rc = (hc <= 16) ? launch_fir_inst<10, 2>(*fm, a, grid, st) : launch_fir_inst<11, 2>(*fm, a, grid, st);
+    a.xin = static_cast<const __nv_bfloat16*>(q.x);
+    a.xgroups = cw.Cin / 8;
+    rc = (hc <= 16) ? launch_fir_inst<10>(*fm, a, grid, st) : launch_fir_inst<11>(*fm, a, grid, st);
   } else
   // run length per activation thread: 4 warps x (8L - 6) valid rows must cover 256 + 2*hc z rows
   if (!aw) rc = launch_inst<9, false>(map, a, grid, st);
