@@ -189,6 +189,12 @@ int bvg_plan_set_profiling(bvg_plan* plan, int enable);
 /* Synchronises the events recorded so far, adds them up, clears the accumulators. */
 int bvg_plan_read_profile(bvg_plan* plan, bvg_profile* out);
 
+/* Experimental: narrow activated AMP layers (C_in, C_out <= max_c, at most 64) take k_amp_fir, which runs both
+ * kaiser-sinc FIRs of Activation1d on the tensor cores (csrc/amp_fir.cuh), instead of k_amp_tc.  Process-wide;
+ * 0 (the default, or the BVG_FIR_MAX_C environment variable at first use) keeps every layer on k_amp_tc.
+ * Returns the previous value. */
+int bvg_set_tc_fir_max_channels(int max_c);
+
 /* ---- per-op entry points (tests, and the reference's own native-op boundary) ---------- */
 
 /* Supersedes anti_alias_activation_cuda.forward(input, up_filter, down_filter, alpha, beta)

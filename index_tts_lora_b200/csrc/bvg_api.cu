@@ -674,6 +674,8 @@ int bvg_plan_set_profiling(bvg_plan* p, int enable) {
   return 0;
 }
 
+int bvg_set_tc_fir_max_channels(int max_c) { return bvg::tc_set_fir_max_c(max_c); }
+
 int bvg_plan_read_profile(bvg_plan* p, bvg_profile* out) {
   BVG_REQUIRE(p && out, "bvg_plan_read_profile: null argument");
   BVG_CUDA(cudaSetDevice(p->device));

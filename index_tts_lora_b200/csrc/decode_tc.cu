@@ -338,10 +338,19 @@ static int launch_fir_inst(const CUtensorMap& map, const TcArgs& a, dim3 grid, c
   return 0;
 }
 
-// narrow activated layers take k_amp_fir (up-sampling FIR on the tensor cores); BVG_FIR_MAX_C=0 disables it
+// narrow activated layers may take k_amp_fir (both FIRs on the tensor cores): opt-in, see bvg_set_tc_fir_max_channels
+static int g_fir_max_c = -1;
+int tc_set_fir_max_c(int v) {
+  const int old = g_fir_max_c < 0 ? 0 : g_fir_max_c;
+  g_fir_max_c = v < 0 ? 0 : v;
+  return old;
+}
 static int fir_max_c() {
-  static const int v = [] { const char* e = getenv("BVG_FIR_MAX_C"); return e ? atoi(e) : 64; }();
-  return v;
+  if (g_fir_max_c < 0) {
+    const char* e = getenv("BVG_FIR_MAX_C");
+    g_fir_max_c = e ? atoi(e) : 0;
+  }
+  return g_fir_max_c;
 }
 
 static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, const ConvW& cw, const ActW* aw,

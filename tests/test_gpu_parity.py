@@ -371,3 +371,49 @@ def test_overlap_recompute_bf16_full_config():
     snr = _snr(whole.cpu(), split.cpu())
     print("overlap-recompute vs whole: SNR", snr)
     assert snr > 60.0, snr
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,d", [(3, 1), (7, 3), (11, 5)])
+@pytest.mark.parametrize("C,T", [(24, 700), (48, 1500), (64, 129), (48, 5), (24, 3)])
+def test_amp_layer_bf16_tensor_core_fir_vs_oracle(k, d, C, T):
+    """Experimental k_amp_fir (both kaiser-sinc FIRs of Activation1d as tcgen05 MMAs, csrc/amp_fir.cuh) against the
+    fp32 oracle: same 35 dB per-layer bar as k_amp_tc, including the sequence-edge rows (T = 3, 5) and ragged tiles."""
+    from index_tts_lora_b200.models import AMPBlock1
+    from index_tts_lora_b200.ops import amp_layer
+    from index_tts_lora_b200 import synth, _lib
+    from index_tts_lora_b200.config import AttrDict
+    O = _oracle()
+    dev = _dev()
+    lib = _lib.load()
+    blk = AMPBlock1(AttrDict(snake_logscale=True), C, k, (d, d, d), activation="snakebeta")
+    sd = synth.synth_state_dict(blk.state_dict(), seed=k * 100 + d, profile="stress")
+    blk.load_state_dict(sd)
+    x = torch.randn(2, C, T, generator=synth._gen(1, f"x{C}{T}"))
+    r = torch.randn(2, C, T, generator=synth._gen(2, f"r{C}{T}"))
+    ref = O.amp_layer(x, sd, "activations.0", "convs1.0", k, d) + r
+    old = lib.bvg_set_tc_fir_max_channels(64)
+    try:
+        y = amp_layer(x.to(dev), blk.convs1[0], blk.activations[0], resid=r.to(dev), precision="bf16").cpu()
+    finally:
+        lib.bvg_set_tc_fir_max_channels(old)
+    y0 = amp_layer(x.to(dev), blk.convs1[0], blk.activations[0], resid=r.to(dev), precision="bf16").cpu()
+    snr = _snr(ref, y)
+    assert snr > 35.0, snr
+    # and it agrees with the default kernel to bf16 rounding
+    assert _snr(y0, y) > 40.0, _snr(y0, y)
+
+
+@pytest.mark.gpu
+def test_full_generator_bf16_tensor_core_fir_snr():
+    """Whole decode with the experimental FIR kernel on the C <= 64 stages: still >= 40 dB on the north-star weights."""
+    from index_tts_lora_b200.config import default_config
+    from index_tts_lora_b200 import _lib
+    lib = _lib.load()
+    old = lib.bvg_set_tc_fir_max_channels(64)
+    try:
+        wav, ref, *_ = _run_case("full_f157_init", default_config(), "bf16")
+    finally:
+        lib.bvg_set_tc_fir_max_channels(old)
+    snr = _snr(ref, wav)
+    print("bf16 + tensor-core FIR SNR dB", snr)
+    assert snr > BF16_SNR_DB, snr
