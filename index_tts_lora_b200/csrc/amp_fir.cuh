@@ -75,11 +75,6 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
   return done != 0;
 }
 
-__device__ __forceinline__ u64 add2(u64 a, u64 b) {
-  u64 d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
 
 // exact re-evaluation of one activated sample z[m] of one channel at a sequence edge (scalar fp32):
 //   z[m] = hb + sum_j dn[j] * s'[clamp(2m+j-5, 0, 2T-1)],  s'[n] = u[n] + nhb*cos(a2*u[n]),
@@ -106,180 +101,6 @@ __device__ __noinline__ float fir_edge_z(const uint8_t* xrow0, int tbox0, int m,
     z = fmaf(a.dn[j], fmaf(nhb, __cosf(a2 * u), u), z);
   }
   return z;
-}
-
-// Lean conv-mode epilogue (no ConvTranspose scatter, one column tile): TMEM -> +bias(+cond) (+resid) (+sum) (x1/div)
-// -> bf16 -> 16-byte stores.  32 accumulator columns per step with the residual / running-sum rows of the step
-// already in flight when the TMEM load is issued; packed f32x2 arithmetic.  Same store rules as epilogue_role.
-template <int NCOL, bool HAS_R, bool HAS_Q>
-__device__ __forceinline__ void epi_step(const TcArgs& a, const float* bs, uint32_t taddr, int cb0, int ngs, int code,
-                                         const __nv_bfloat16* resid, const __nv_bfloat16* accin, __nv_bfloat16* outp,
-                                         int rowoff, int gstride, u64 rdiv2) {
-  constexpr int NG = NCOL / 8;
-  uint4 rr[HAS_R ? NG : 1], qq[HAS_Q ? NG : 1];
-  const int o0 = (cb0 >> 3) * gstride + rowoff;
-  if (code == 1) {
-    if constexpr (HAS_R) {
-#pragma unroll
-      for (int kk = 0; kk < NG; ++kk)      // dead groups re-read the last live one (no predicated array slots)
-        rr[kk] = *reinterpret_cast<const uint4*>(resid + o0 + min(kk, ngs - 1) * gstride);
-    }
-    if constexpr (HAS_Q) {
-#pragma unroll
-      for (int kk = 0; kk < NG; ++kk)
-        qq[kk] = *reinterpret_cast<const uint4*>(accin + o0 + min(kk, ngs - 1) * gstride);
-    }
-  }
-  uint32_t v[NCOL];
-  if constexpr (NCOL == 32) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr + (uint32_t)cb0));
-  } else {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr + (uint32_t)cb0));
-  }
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-  if (code == 0) return;
-#pragma unroll
-  for (int kk = 0; kk < NG; ++kk) {
-    if (kk >= ngs) break;
-    uint4 o = make_uint4(0, 0, 0, 0);
-    if (code == 1) {
-      const ulonglong2 b01 = *reinterpret_cast<const ulonglong2*>(bs + cb0 + kk * 8);
-      const ulonglong2 b23 = *reinterpret_cast<const ulonglong2*>(bs + cb0 + kk * 8 + 4);
-      u64 f[4];
-      f[0] = add2(pk(__uint_as_float(v[kk * 8 + 0]), __uint_as_float(v[kk * 8 + 1])), b01.x);
-      f[1] = add2(pk(__uint_as_float(v[kk * 8 + 2]), __uint_as_float(v[kk * 8 + 3])), b01.y);
-      f[2] = add2(pk(__uint_as_float(v[kk * 8 + 4]), __uint_as_float(v[kk * 8 + 5])), b23.x);
-      f[3] = add2(pk(__uint_as_float(v[kk * 8 + 6]), __uint_as_float(v[kk * 8 + 7])), b23.y);
-      if constexpr (HAS_R) {
-        f[0] = add2(f[0], bf2_to_f2(rr[kk].x)); f[1] = add2(f[1], bf2_to_f2(rr[kk].y));
-        f[2] = add2(f[2], bf2_to_f2(rr[kk].z)); f[3] = add2(f[3], bf2_to_f2(rr[kk].w));
-      }
-      if constexpr (HAS_Q) {
-        f[0] = add2(f[0], bf2_to_f2(qq[kk].x)); f[1] = add2(f[1], bf2_to_f2(qq[kk].y));
-        f[2] = add2(f[2], bf2_to_f2(qq[kk].z)); f[3] = add2(f[3], bf2_to_f2(qq[kk].w));
-      }
-      if (a.div != 1.0f) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) f[e] = mul2(f[e], rdiv2);
-      }
-      uint32_t w[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float lo, hi;
-        upk(f[e], lo, hi);
-        __nv_bfloat162 pb = __floats2bfloat162_rn(lo, hi);
-        w[e] = *reinterpret_cast<uint32_t*>(&pb);
-      }
-      o = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-    *reinterpret_cast<uint4*>(outp + o0 + kk * gstride) = o;
-  }
-}
-
-template <bool HAS_R, bool HAS_Q>
-__device__ __forceinline__ void epilogue_fir_t(const TcArgs& a, float* bias_s, const int* prefix, uint32_t bar_accfull0,
-                                             uint32_t bar_accempty0, uint32_t tmem, int nacc, int total_tiles, int q,
-                                             int lane, int etid) {
-  const int n_tile = a.n_tile;
-  const int cg_total = a.Cout >> 3;
-  const int ng = min(n_tile >> 3, cg_total);
-  const int gstride = a.Tstride * 8;
-  const float rdiv = 1.0f / a.div;
-  const u64 rdiv2 = pk(rdiv, rdiv);
-  TileCursor cur{prefix};
-  int it = 0, last_b = -1;
-  for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++it) {
-    int b, t0, nt;
-    cur.locate(w, 1, b, t0, nt);
-    const int T = a.lengths ? a.lengths[b] * a.rate : a.Tmax;
-    const int as = (nacc == 2) ? (it & 1) : 0;
-    const int ause = (nacc == 2) ? (it >> 1) : it;
-    if (last_b < 0 || (a.bias_b && b != last_b)) {                     // bias row changes with the utterance only
-      asm volatile("bar.sync 1, 128;" ::: "memory");                   // every warp is done with the previous row
-      for (int i = etid; i < n_tile; i += 128) {
-        float v = 0.f;
-        if (i < a.Cout) {
-          v = __ldg(a.bias + i);
-          if (a.bias_b) v += __ldg(a.bias_b + (size_t)b * a.bias_b_stride + i);
-        }
-        bias_s[i] = v;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      last_b = b;
-    }
-    const size_t ubase = (size_t)b * cg_total * a.Tstride * 8;
-    const __nv_bfloat16* resid = a.resid ? a.resid + ubase : nullptr;
-    const __nv_bfloat16* accin = a.acc_in ? a.acc_in + ubase : nullptr;
-    __nv_bfloat16* outp = a.out + ubase;
-    if (resid || accin) {
-      // warm L2 with this tile's residual / running-sum rows while its MMAs are still running
-#pragma unroll 1
-      for (int mb = 0; mb < 2; ++mb) {
-        const int t = t0 + mb * 128 + q * 32 + lane;
-        if (t >= T) continue;
-        int o = t * 8;
-#pragma unroll 1
-        for (int g = 0; g < ng; ++g, o += gstride) {
-          if (resid) asm volatile("prefetch.global.L2 [%0];" ::"l"(resid + o));
-          if (accin) asm volatile("prefetch.global.L2 [%0];" ::"l"(accin + o));
-        }
-      }
-    }
-    if (q == 0) mbar_wait_relaxed(bar_accfull0 + 8 * as, ause & 1, 100);
-    asm volatile("bar.sync 2, 128;" ::: "memory");
-    tc_fence_after();
-    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * n_tile);
-#pragma unroll 1
-    for (int mb = 0; mb < ((a.dbg & 8) ? 0 : 2); ++mb) {
-      const int t = t0 + mb * 128 + q * 32 + lane;
-      const int code = (t >= a.Tmax || t < a.st_lo || t >= a.st_hi) ? 0 : (t < T ? 1 : 2);
-#pragma unroll 1
-      constexpr int STEP = HAS_Q ? 16 : 32;       // the running-sum variant keeps fewer rows in flight (registers)
-      for (int cb0 = 0; cb0 < n_tile; cb0 += STEP) {
-        const int ngs = ng - (cb0 >> 3);
-        if (ngs <= 0) break;                                            // warp-uniform
-        if (n_tile - cb0 >= STEP)
-          epi_step<STEP, HAS_R, HAS_Q>(a, bias_s, taddr + (uint32_t)(mb * n_tile), cb0, ngs, code, resid, accin, outp, t * 8, gstride, rdiv2);
-        else
-          epi_step<16, HAS_R, HAS_Q>(a, bias_s, taddr + (uint32_t)(mb * n_tile), cb0, ngs, code, resid, accin, outp, t * 8, gstride, rdiv2);
-      }
-    }
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar_accempty0 + 8 * as);
-    // un-activated consumers (ConvTranspose1d) read one row past the end: keep rows [T, T+8) zero
-    // when the utterance ends exactly on this tile's boundary (otherwise they were zeroed above)
-    if (T == t0 + M_TILE && T < a.Tmax && T < a.st_hi && q == 0) {
-      for (int i = lane; i < ng * 8; i += 32) {
-        const int g = i >> 3, r = T + (i & 7);
-        if (r < a.Tmax)
-          *reinterpret_cast<uint4*>(a.out + (((size_t)b * cg_total + g) * a.Tstride + r) * 8) = make_uint4(0, 0, 0, 0);
-      }
-    }
-  }
-}
-
-__device__ __forceinline__ void epilogue_fir(const TcArgs& a, float* bias_s, const int* prefix, uint32_t bar_accfull0,
-                                             uint32_t bar_accempty0, uint32_t tmem, int nacc, int total_tiles, int q,
-                                             int lane, int etid) {
-  if (a.resid) {
-    if (a.acc_in) epilogue_fir_t<true, true>(a, bias_s, prefix, bar_accfull0, bar_accempty0, tmem, nacc, total_tiles, q, lane, etid);
-    else epilogue_fir_t<true, false>(a, bias_s, prefix, bar_accfull0, bar_accempty0, tmem, nacc, total_tiles, q, lane, etid);
-  } else {
-    if (a.acc_in) epilogue_fir_t<false, true>(a, bias_s, prefix, bar_accfull0, bar_accempty0, tmem, nacc, total_tiles, q, lane, etid);
-    else epilogue_fir_t<false, false>(a, bias_s, prefix, bar_accfull0, bar_accempty0, tmem, nacc, total_tiles, q, lane, etid);
-  }
 }
 
 __device__ __forceinline__ void umma_ts_f16(uint32_t tmem_d, uint32_t tmem_a, u64 bdesc, uint32_t idesc, uint32_t acc) {
@@ -693,7 +514,7 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
   } else {
     // ===================== epilogue warps =====================
     reg_inc<120>();
-    epilogue_fir(a, bias_s, prefix, BAR_ACCFULL(0), BAR_ACCEMPTY(0), tmem, nacc, total_tiles, warp & 3, lane,
+    epilogue_fir<32>(a, bias_s, prefix, BAR_ACCFULL(0), BAR_ACCEMPTY(0), tmem, nacc, total_tiles, warp & 3, lane,
                  threadIdx.x - WARP_EPI * 32);
   }
   tc_fence_before();
