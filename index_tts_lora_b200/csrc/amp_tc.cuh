@@ -579,38 +579,42 @@ __device__ __forceinline__ void epi_step(const TcArgs& a, const float* bs, uint3
   }
 }
 
-template <bool HAS_R, bool HAS_Q, int STEPW>
+template <bool HAS_R, bool HAS_Q, int STEPW, bool MULTI>
 __device__ __forceinline__ void epilogue_fir_t(const TcArgs& a, float* bias_s, const int* prefix, uint32_t bar_accfull0,
                                              uint32_t bar_accempty0, uint32_t tmem, int nacc, int total_tiles, int q,
                                              int lane, int etid) {
-  const int n_tile = a.n_tile;
+  const int n_tile = a.n_tile, n_tiles = MULTI ? a.n_tiles : 1;   // MULTI = several column tiles per time tile
   const int cg_total = a.Cout >> 3;
-  const int ng = min(n_tile >> 3, cg_total);
   const int gstride = a.Tstride * 8;
   const float rdiv = 1.0f / a.div;
   const u64 rdiv2 = pk(rdiv, rdiv);
   TileCursor cur{prefix};
-  int it = 0, last_b = -1;
+  int it = 0, last_b = -1, last_nt = -1;
   for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++it) {
     int b, t0, nt;
-    cur.locate(w, 1, b, t0, nt);
+    cur.locate(w, n_tiles, b, t0, nt);
     const int T = a.lengths ? a.lengths[b] * a.rate : a.Tmax;
     const int as = (nacc == 2) ? (it & 1) : 0;
     const int ause = (nacc == 2) ? (it >> 1) : it;
-    if (last_b < 0 || (a.bias_b && b != last_b)) {                     // bias row changes with the utterance only
+    if (!MULTI) nt = 0;
+    const int cgn0 = nt * (n_tile >> 3);                               // first column group of this tile
+    const int ng = min(n_tile >> 3, cg_total - cgn0);                  // live column groups
+    if (last_b < 0 || nt != last_nt || (a.bias_b && b != last_b)) {    // bias row changes with (utterance, column tile)
       asm volatile("bar.sync 1, 128;" ::: "memory");                   // every warp is done with the previous row
       for (int i = etid; i < n_tile; i += 128) {
+        const int co = nt * n_tile + i;
         float v = 0.f;
-        if (i < a.Cout) {
-          v = __ldg(a.bias + i);
-          if (a.bias_b) v += __ldg(a.bias_b + (size_t)b * a.bias_b_stride + i);
+        if (co < a.Cout) {
+          v = __ldg(a.bias + co);
+          if (a.bias_b) v += __ldg(a.bias_b + (size_t)b * a.bias_b_stride + co);
         }
         bias_s[i] = v;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       last_b = b;
+      last_nt = nt;
     }
-    const size_t ubase = (size_t)b * cg_total * a.Tstride * 8;
+    const size_t ubase = ((size_t)b * cg_total + cgn0) * a.Tstride * 8;   // this (utterance, column tile)'s first group
     const __nv_bfloat16* resid = a.resid ? a.resid + ubase : nullptr;
     const __nv_bfloat16* accin = a.acc_in ? a.acc_in + ubase : nullptr;
     __nv_bfloat16* outp = a.out + ubase;
@@ -636,8 +640,8 @@ __device__ __forceinline__ void epilogue_fir_t(const TcArgs& a, float* bias_s, c
     for (int mb = 0; mb < ((a.dbg & 8) ? 0 : 2); ++mb) {
       const int t = t0 + mb * 128 + q * 32 + lane;
       const int code = (t >= a.Tmax || t < a.st_lo || t >= a.st_hi) ? 0 : (t < T ? 1 : 2);
-#pragma unroll 1
       constexpr int STEP = (HAS_Q || STEPW == 16) ? 16 : 32;   // fewer rows in flight where registers are short
+#pragma unroll 1
       for (int cb0 = 0; cb0 < n_tile; cb0 += STEP) {
         const int ngs = ng - (cb0 >> 3);
         if (ngs <= 0) break;                                            // warp-uniform
@@ -656,22 +660,22 @@ __device__ __forceinline__ void epilogue_fir_t(const TcArgs& a, float* bias_s, c
       for (int i = lane; i < ng * 8; i += 32) {
         const int g = i >> 3, r = T + (i & 7);
         if (r < a.Tmax)
-          *reinterpret_cast<uint4*>(a.out + (((size_t)b * cg_total + g) * a.Tstride + r) * 8) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(a.out + (((size_t)b * cg_total + cgn0 + g) * a.Tstride + r) * 8) = make_uint4(0, 0, 0, 0);
       }
     }
   }
 }
 
-template <int STEPW>
+template <int STEPW, bool MULTI = false>
 __device__ __forceinline__ void epilogue_fir(const TcArgs& a, float* bias_s, const int* prefix, uint32_t bar_accfull0,
                                              uint32_t bar_accempty0, uint32_t tmem, int nacc, int total_tiles, int q,
                                              int lane, int etid) {
   if (a.resid) {
-    if (a.acc_in) epilogue_fir_t<true, true, STEPW>(a, bias_s, prefix, bar_accfull0, bar_accempty0, tmem, nacc, total_tiles, q, lane, etid);
-    else epilogue_fir_t<true, false, STEPW>(a, bias_s, prefix, bar_accfull0, bar_accempty0, tmem, nacc, total_tiles, q, lane, etid);
+    if (a.acc_in) epilogue_fir_t<true, true, STEPW, MULTI>(a, bias_s, prefix, bar_accfull0, bar_accempty0, tmem, nacc, total_tiles, q, lane, etid);
+    else epilogue_fir_t<true, false, STEPW, MULTI>(a, bias_s, prefix, bar_accfull0, bar_accempty0, tmem, nacc, total_tiles, q, lane, etid);
   } else {
-    if (a.acc_in) epilogue_fir_t<false, true, STEPW>(a, bias_s, prefix, bar_accfull0, bar_accempty0, tmem, nacc, total_tiles, q, lane, etid);
-    else epilogue_fir_t<false, false, STEPW>(a, bias_s, prefix, bar_accfull0, bar_accempty0, tmem, nacc, total_tiles, q, lane, etid);
+    if (a.acc_in) epilogue_fir_t<false, true, STEPW, MULTI>(a, bias_s, prefix, bar_accfull0, bar_accempty0, tmem, nacc, total_tiles, q, lane, etid);
+    else epilogue_fir_t<false, false, STEPW, MULTI>(a, bias_s, prefix, bar_accfull0, bar_accempty0, tmem, nacc, total_tiles, q, lane, etid);
   }
 }
 
@@ -917,9 +921,12 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
   } else {
     // ===================== epilogue warps: TMEM -> (+bias, +resid, +sum, /div) -> bf16 -> HBM ====
     reg_dec<64>();
-    if (a.up == 0 && n_tiles == 1 && !(a.dbg & 1024))   // conv mode, one column tile: the lean packed-math epilogue
-      epilogue_fir<16>(a, bias_s, prefix, BAR_ACCFULL(0), BAR_ACCEMPTY(0), tmem, nacc, total_tiles, warp & 3, lane,
-                       threadIdx.x - (NW_ACT + 4) * 32);
+    if (a.up == 0 && n_tiles == 1 && !(a.dbg & 1024))   // conv mode: the lean packed-math epilogue
+      epilogue_fir<16, false>(a, bias_s, prefix, BAR_ACCFULL(0), BAR_ACCEMPTY(0), tmem, nacc, total_tiles, warp & 3, lane,
+                              threadIdx.x - (NW_ACT + 4) * 32);
+    else if (a.up == 0 && !(a.dbg & 1024))
+      epilogue_fir<16, true>(a, bias_s, prefix, BAR_ACCFULL(0), BAR_ACCEMPTY(0), tmem, nacc, total_tiles, warp & 3, lane,
+                             threadIdx.x - (NW_ACT + 4) * 32);
     else
       epilogue_role(a, bias_s, prefix, BAR_ACCFULL(0), BAR_ACCEMPTY(0), tmem, nacc, total_tiles, extra, warp & 3, lane,
                     threadIdx.x - (NW_ACT + 4) * 32);
