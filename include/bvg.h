@@ -195,6 +195,14 @@ int bvg_plan_read_profile(bvg_plan* plan, bvg_profile* out);
  * Returns the previous value. */
 int bvg_set_tc_fir_max_channels(int max_c);
 
+/* bf16 path: AMP layers with C_in >= min_c run in split form — Activation1d once per layer in a streaming kernel
+ * (csrc/act_blk.cuh) into an L2-sized scratch buffer, then the dilated conv as the same tcgen05 kernel without its
+ * activation role — instead of the fused kernel, which repeats the activation for every 256-wide column tile of the
+ * conv (3x at C = 768, 2x at C = 384).  The z rows, and therefore the output, are bit-identical in both forms.
+ * Process-wide; 0 = every layer fused.  Default: the BVG_SPLIT_MIN_C environment variable at first use, else the
+ * built-in threshold.  Returns the previous value. */
+int bvg_set_tc_split_min_channels(int min_c);
+
 /* ---- per-op entry points (tests, and the reference's own native-op boundary) ---------- */
 
 /* Supersedes anti_alias_activation_cuda.forward(input, up_filter, down_filter, alpha, beta)

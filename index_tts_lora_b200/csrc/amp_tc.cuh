@@ -57,7 +57,10 @@ constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
 constexpr int OFF_X = (OFF_TMEM + 16 + 127) / 128 * 128;
 __host__ __device__ constexpr int off_z(int nx) { return OFF_X + nx * X_BUF_BYTES; }
 __host__ __device__ constexpr int off_w(int nx, int nz) { return off_z(nx) + nz * Z_BUF_BYTES; }
-__host__ __device__ constexpr int smem_bytes(int nx, int nz, int wst) { return off_w(nx, nz) + wst * W_STAGE_BYTES; }
+constexpr int R_SLOTS = 16;                       // 16-byte rows per epilogue thread staged for the residual / running sum
+constexpr int R_STAGE_BYTES = R_SLOTS * 128 * 16; // 32 KB: [slot][epilogue thread][16 B]
+__host__ __device__ constexpr int off_r(int nx, int nz, int wst) { return off_w(nx, nz) + wst * W_STAGE_BYTES; }
+__host__ __device__ constexpr int smem_bytes(int nx, int nz, int wst) { return off_r(nx, nz, wst) + R_STAGE_BYTES; }
 
 struct TcArgs {
   const __nv_bfloat16* wt;     // [ntile][chunk][tap][4][n_tile][8] bf16
@@ -132,6 +135,9 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ u64 make_sdesc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   // SWIZZLE_NONE K-major: SBO = stride between 8-row groups, LBO = stride between the two
@@ -238,42 +244,60 @@ __device__ __forceinline__ void act_run(const uint32_t* __restrict__ xk, uint32_
     if (EDGE) r = r < 0 ? 0 : (r > XRA - 1 ? XRA - 1 : r);   // interior runs: 1 <= r <= 8L*4+35 < XRA
     xw[i] = bf2_to_f2(xk[r * 4]);
   }
+  // QB input positions per batch = 2*QB independent FMA chains in flight (even / odd phase of each): the chains of
+  // one up-sampled sample are 6 dependent FFMA2s, and a warp that walks them two at a time stalls on the FMA latency
+  constexpr int QB = 3;
 #pragma unroll
-  for (int u = 0; u < 2 * L; ++u) {
-    u64 y;
-    if ((u & 1) == 0) {                // n even: taps f[11-2i] on x[q-3+i]
-      const int i0 = u / 2;
-      y = mul2(k.upE[0], xw[i0]);
+  for (int q0 = 0; q0 < L; q0 += QB) {
+    u64 ye[QB], yo[QB];
 #pragma unroll
-      for (int i = 1; i < 6; ++i) y = fma2(k.upE[i], xw[i0 + i], y);
-    } else {                           // n odd: taps f[10-2i] on x[q-2+i]
-      const int i0 = (u - 1) / 2 + 1;
-      y = mul2(k.upO[0], xw[i0]);
+    for (int qq = 0; qq < QB; ++qq)
+      if (q0 + qq < L) {
+        ye[qq] = mul2(k.upE[0], xw[q0 + qq]);          // n even: taps f[11-2i] on x[q-3+i]
+        yo[qq] = mul2(k.upO[0], xw[q0 + qq + 1]);      // n odd:  taps f[10-2i] on x[q-2+i]
+      }
 #pragma unroll
-      for (int i = 1; i < 6; ++i) y = fma2(k.upO[i], xw[i0 + i], y);
-    }
-    u64 sn = snake_s(y, k);
-    if (EDGE) {
-      const int n = 2 * m0 + u;
-      if (n < 0) sn = s_first;
-      else if (n > 2 * T - 1) sn = s_last;
-    }
-    sv[u] = sn;
+    for (int i = 1; i < 6; ++i)
+#pragma unroll
+      for (int qq = 0; qq < QB; ++qq)
+        if (q0 + qq < L) {
+          ye[qq] = fma2(k.upE[i], xw[q0 + qq + i], ye[qq]);
+          yo[qq] = fma2(k.upO[i], xw[q0 + qq + 1 + i], yo[qq]);
+        }
+#pragma unroll
+    for (int qq = 0; qq < QB; ++qq)
+      if (q0 + qq < L) {
+        u64 se = snake_s(ye[qq], k), so = snake_s(yo[qq], k);
+        if (EDGE) {
+          const int n = 2 * (m0 + q0 + qq);
+          if (n < 0) se = s_first;
+          else if (n > 2 * T - 1) se = s_last;
+          if (n + 1 < 0) so = s_first;
+          else if (n + 1 > 2 * T - 1) so = s_last;
+        }
+        sv[2 * (q0 + qq)] = se;
+        sv[2 * (q0 + qq) + 1] = so;
+      }
   }
   u64 sb[5], sa[6];
 #pragma unroll
   for (int j = 0; j < 5; ++j) sb[j] = shfl64(sv[2 * L - 5 + j], (lane + 28) & 31);
 #pragma unroll
   for (int j = 0; j < 6; ++j) sa[j] = shfl64(sv[j], (lane + 4) & 31);
+  u64 zz[L];                             // tap-outer: L independent accumulation chains
+#pragma unroll
+  for (int r = 0; r < L; ++r) zz[r] = k.hb;
+#pragma unroll
+  for (int j = 0; j < 12; ++j)
+#pragma unroll
+    for (int r = 0; r < L; ++r) {
+      const int q = 2 * r + j - 5;       // index into this run's own samples
+      const u64 sj = q < 0 ? sb[5 + q] : (q < 2 * L ? sv[q] : sa[q - 2 * L]);
+      zz[r] = fma2(k.dn[j], sj, zz[r]);
+    }
 #pragma unroll
   for (int r = 0; r < L; ++r) {
-    u64 z = k.hb;
-#pragma unroll
-    for (int j = 0; j < 12; ++j) {
-      const int q = 2 * r + j - 5;     // index into this run's own samples
-      const u64 sj = q < 0 ? sb[5 + q] : (q < 2 * L ? sv[q] : sa[q - 2 * L]);
-      z = fma2(k.dn[j], sj, z);
-    }
+    const u64 z = zz[r];
     float z0, z1;
     upk(z, z0, z1);
     if (EDGE) {
@@ -287,7 +311,8 @@ __device__ __forceinline__ void act_run(const uint32_t* __restrict__ xk, uint32_
   }
 }
 
-__device__ __forceinline__ void load_taps(ActCtx& k, const TcArgs& a) {
+template <class Args>
+__device__ __forceinline__ void load_taps(ActCtx& k, const Args& a) {
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     k.upE[i] = pk(a.up2[11 - 2 * i], a.up2[11 - 2 * i]);
@@ -299,9 +324,9 @@ __device__ __forceinline__ void load_taps(ActCtx& k, const TcArgs& a) {
 
 // Sequence-edge tiles (2 per utterance) take this out-of-line copy so that none of its clamp /
 // select arithmetic is hoisted into the interior path.
-template <int L>
+template <int L, class Args>
 __device__ __noinline__ void act_run_edge(const uint32_t* xk, uint32_t* zk, int rowS, uint32_t smask, int m0,
-                                          int xlo, int T, u64 a2, u64 nhb, const TcArgs& a, int lane) {
+                                          int xlo, int T, u64 a2, u64 nhb, const Args& a, int lane) {
   ActCtx k;
   load_taps(k, a);
   k.a2 = a2;
@@ -680,6 +705,231 @@ __device__ __forceinline__ void epilogue_fir(const TcArgs& a, float* bias_s, con
 }
 
 
+// ------------------------------------------------------------------------------ pipelined conv-mode epilogue
+// The residual / running-sum rows of a tile were written several launches ago and are not in L2 any more.  Loading
+// them into registers right before the TMEM read leaves ~4 KB in flight per SM (128 threads x 2 x 16 B — the epilogue
+// warps have 64 registers), and per-launch events showed every layer with a residual 50-110 us slower than its twin
+// without one: the epilogue, not the activation or the MMAs, set the pace.  Here the rows go through shared memory
+// instead: each epilogue thread owns R_SLOTS 16-byte slots ([slot][thread] layout, conflict-free), fills them with
+// cp.async — the first LA steps before it even waits for the accumulator, the others as steps retire — and reads a
+// step's rows back with one LDS each just before the math.  32 KB per SM in flight, no registers held; the rows of the
+// NEXT tile are L2-prefetched meanwhile.
+template <int NG, bool HAS_R, bool HAS_Q>
+__device__ __forceinline__ void epi_rows_finish(const uint4* rr, const uint4* qq, const TcArgs& a, const float* bs,
+                                                uint32_t taddr, int cb0, int ngs, int code, __nv_bfloat16* outp, int o0,
+                                                int gstride, u64 rdiv2) {
+  uint32_t v[NG * 8];
+  if constexpr (NG == 4) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr + (uint32_t)cb0));
+  } else {
+    static_assert(NG == 2, "epilogue step = 16 or 32 accumulator columns");
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr + (uint32_t)cb0));
+  }
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  if (code == 0) return;
+#pragma unroll
+  for (int kk = 0; kk < NG; ++kk) {
+    if (kk >= ngs) break;
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (code == 1) {
+      const ulonglong2 b01 = *reinterpret_cast<const ulonglong2*>(bs + cb0 + kk * 8);
+      const ulonglong2 b23 = *reinterpret_cast<const ulonglong2*>(bs + cb0 + kk * 8 + 4);
+      u64 f[4];
+      f[0] = add2(pk(__uint_as_float(v[kk * 8 + 0]), __uint_as_float(v[kk * 8 + 1])), b01.x);
+      f[1] = add2(pk(__uint_as_float(v[kk * 8 + 2]), __uint_as_float(v[kk * 8 + 3])), b01.y);
+      f[2] = add2(pk(__uint_as_float(v[kk * 8 + 4]), __uint_as_float(v[kk * 8 + 5])), b23.x);
+      f[3] = add2(pk(__uint_as_float(v[kk * 8 + 6]), __uint_as_float(v[kk * 8 + 7])), b23.y);
+      if constexpr (HAS_R) {
+        f[0] = add2(f[0], bf2_to_f2(rr[kk].x)); f[1] = add2(f[1], bf2_to_f2(rr[kk].y));
+        f[2] = add2(f[2], bf2_to_f2(rr[kk].z)); f[3] = add2(f[3], bf2_to_f2(rr[kk].w));
+      }
+      if constexpr (HAS_Q) {
+        f[0] = add2(f[0], bf2_to_f2(qq[kk].x)); f[1] = add2(f[1], bf2_to_f2(qq[kk].y));
+        f[2] = add2(f[2], bf2_to_f2(qq[kk].z)); f[3] = add2(f[3], bf2_to_f2(qq[kk].w));
+      }
+      if (a.div != 1.0f) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) f[i] = mul2(f[i], rdiv2);
+      }
+      uint32_t w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float lo, hi;
+        upk(f[i], lo, hi);
+        __nv_bfloat162 pb = __floats2bfloat162_rn(lo, hi);
+        w[i] = *reinterpret_cast<uint32_t*>(&pb);
+      }
+      o = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    if (!(a.dbg & 64)) *reinterpret_cast<uint4*>(outp + o0 + kk * gstride) = o;
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// NG channel groups (8 accumulator columns each) per step; LA steps of row copies in flight
+// (LA * NG * (HAS_R + HAS_Q) = R_SLOTS slots per thread).
+template <int NG, bool HAS_R, bool HAS_Q, bool MULTI>
+__device__ __forceinline__ void epilogue_pipe_t(const TcArgs& a, float* bias_s, uint8_t* rstage, const int* prefix,
+                                                uint32_t bar_accfull0, uint32_t bar_accempty0, uint32_t tmem, int nacc,
+                                                int total_tiles, int q, int lane, int etid) {
+  constexpr int NSTREAM = (HAS_R ? 1 : 0) + (HAS_Q ? 1 : 0);
+  constexpr int LA = NSTREAM ? R_SLOTS / (NG * NSTREAM) : 1;
+  const int n_tile = a.n_tile, n_tiles = MULTI ? a.n_tiles : 1;
+  const int cg_total = a.Cout >> 3;
+  const int gstride = a.Tstride * 8;
+  const float rdiv = 1.0f / a.div;
+  const u64 rdiv2 = pk(rdiv, rdiv);
+  // slot (step ring position r, stream st, group kk) of this thread
+  uint8_t* my_stage = rstage + etid * 16;
+  const uint32_t my_stage_u = smem_u32(my_stage);
+  auto slot_off = [&](int r, int st, int kk) { return (uint32_t)(((r * NSTREAM + st) * NG + kk) * 128 * 16); };
+  TileCursor cur{prefix};
+  int it = 0, last_b = -1, last_nt = -1;
+  int T_next = 0;                      // length of the next tile's utterance, requested one tile early (L2 round trip)
+  // L2 prefetch of one tile's residual / running-sum rows (this thread's two rows, all live column groups)
+  auto prefetch_tile = [&](int w) {
+    if (w >= total_tiles) return;
+    TileCursor c2 = cur;
+    int b, t0, nt;
+    c2.locate(w, n_tiles, b, t0, nt);
+    T_next = a.lengths ? __ldg(a.lengths + b) * a.rate : a.Tmax;
+    if (!(HAS_R || HAS_Q) || (a.dbg & 128)) return;
+    if (!MULTI) nt = 0;
+    const int cgn0 = nt * (n_tile >> 3);
+    const int ng = min(n_tile >> 3, cg_total - cgn0);
+    const size_t ubase = ((size_t)b * cg_total + cgn0) * a.Tstride * 8;
+#pragma unroll 1
+    for (int mb = 0; mb < 2; ++mb) {
+      const int t = t0 + mb * 128 + q * 32 + lane;
+      if (t >= a.Tmax) continue;       // rows past the utterance's end are inside the buffer: no need to wait for T_next
+      size_t o = ubase + (size_t)t * 8;
+#pragma unroll 1
+      for (int g = 0; g < ng; ++g, o += gstride) {
+        if constexpr (HAS_R) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.resid + o));
+        if constexpr (HAS_Q) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.acc_in + o));
+      }
+    }
+  };
+  prefetch_tile(blockIdx.x);
+  for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++it) {
+    int b, t0, nt;
+    cur.locate(w, n_tiles, b, t0, nt);
+    const int T = T_next;
+    const int as = (nacc == 2) ? (it & 1) : 0;
+    const int ause = (nacc == 2) ? (it >> 1) : it;
+    if (!MULTI) nt = 0;
+    const int cgn0 = nt * (n_tile >> 3);                               // first column group of this tile
+    const int ng = min(n_tile >> 3, cg_total - cgn0);                  // live column groups
+    if (last_b < 0 || nt != last_nt || (a.bias_b && b != last_b)) {    // bias row changes with (utterance, column tile)
+      asm volatile("bar.sync 1, 128;" ::: "memory");                   // every warp is done with the previous row
+      for (int i = etid; i < n_tile; i += 128) {
+        const int co = nt * n_tile + i;
+        float v = 0.f;
+        if (co < a.Cout) {
+          v = __ldg(a.bias + co);
+          if (a.bias_b) v += __ldg(a.bias_b + (size_t)b * a.bias_b_stride + co);
+        }
+        bias_s[i] = v;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      last_b = b;
+      last_nt = nt;
+    }
+    const size_t ubase = ((size_t)b * cg_total + cgn0) * a.Tstride * 8;   // this (utterance, column tile)'s first group
+    const __nv_bfloat16* resid = HAS_R ? a.resid + ubase : nullptr;
+    const __nv_bfloat16* accin = HAS_Q ? a.acc_in + ubase : nullptr;
+    __nv_bfloat16* outp = a.out + ubase;
+    // steps: s -> (mb, cs); spm steps per M block
+    const int spm = (ng + NG - 1) / NG;
+    const int nst = (a.dbg & 8) ? 0 : 2 * spm;
+    const int tr0 = t0 + q * 32 + lane, tr1 = tr0 + 128;
+    const int code0 = (tr0 >= a.Tmax || tr0 < a.st_lo || tr0 >= a.st_hi) ? 0 : (tr0 < T ? 1 : 2);
+    const int code1 = (tr1 >= a.Tmax || tr1 < a.st_lo || tr1 >= a.st_hi) ? 0 : (tr1 < T ? 1 : 2);
+    // request the rows of step s into ring position s % LA (one commit group per step, empty ones included)
+    auto issue = [&](int s) {
+      if constexpr (NSTREAM > 0) {
+        if (s < nst) {
+          const int mb = s >= spm ? 1 : 0, cs = s - mb * spm;
+          if ((mb ? code1 : code0) == 1 && !(a.dbg & 32)) {
+            const int o0 = cs * NG * gstride + (mb ? tr1 : tr0) * 8, ngs = ng - cs * NG, r = s % LA;
+#pragma unroll
+            for (int kk = 0; kk < NG; ++kk) {          // dead groups re-read the last live one
+              const int o = o0 + min(kk, ngs - 1) * gstride;
+              if constexpr (HAS_R) cp_async16(my_stage_u + slot_off(r, 0, kk), resid + o);
+              if constexpr (HAS_Q) cp_async16(my_stage_u + slot_off(r, HAS_R ? 1 : 0, kk), accin + o);
+            }
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+    };
+#pragma unroll 1
+    for (int s = 0; s < LA; ++s) issue(s);
+    prefetch_tile(w + gridDim.x);
+    if (q == 0) mbar_wait_relaxed(bar_accfull0 + 8 * as, ause & 1, 100);
+    asm volatile("bar.sync 2, 128;" ::: "memory");
+    tc_fence_after();
+    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * n_tile);
+#pragma unroll 1
+    for (int s = 0; s < nst; ++s) {
+      const int mb = s >= spm ? 1 : 0, cs = s - mb * spm;
+      uint4 rr[NG], qq[NG];
+      if constexpr (NSTREAM > 0) {
+        cp_async_wait<LA - 1>();                       // step s's group (and every older one) has landed
+        const int r = s % LA;
+#pragma unroll
+        for (int kk = 0; kk < NG; ++kk) {
+          if constexpr (HAS_R) rr[kk] = *reinterpret_cast<const uint4*>(my_stage + slot_off(r, 0, kk));
+          if constexpr (HAS_Q) qq[kk] = *reinterpret_cast<const uint4*>(my_stage + slot_off(r, HAS_R ? 1 : 0, kk));
+        }
+      }
+      epi_rows_finish<NG, HAS_R, HAS_Q>(rr, qq, a, bias_s, taddr + (uint32_t)(mb * n_tile), cs * NG * 8, ng - cs * NG,
+                                        mb ? code1 : code0, outp, cs * NG * gstride + (mb ? tr1 : tr0) * 8, gstride,
+                                        rdiv2);
+      issue(s + LA);
+    }
+    if constexpr (NSTREAM > 0) cp_async_wait<0>();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_accempty0 + 8 * as);
+    // un-activated consumers (ConvTranspose1d) read one row past the end: keep rows [T, T+8) zero
+    // when the utterance ends exactly on this tile's boundary (otherwise they were zeroed above)
+    if (T == t0 + M_TILE && T < a.Tmax && T < a.st_hi && q == 0) {
+      for (int i = lane; i < ng * 8; i += 32) {
+        const int g = i >> 3, r = T + (i & 7);
+        if (r < a.Tmax)
+          *reinterpret_cast<uint4*>(a.out + (((size_t)b * cg_total + cgn0 + g) * a.Tstride + r) * 8) = make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
+}
+
+template <bool MULTI>
+__device__ __forceinline__ void epilogue_pipe(const TcArgs& a, float* bias_s, uint8_t* rstage, const int* prefix,
+                                              uint32_t bar_accfull0, uint32_t bar_accempty0, uint32_t tmem, int nacc,
+                                              int total_tiles, int q, int lane, int etid) {
+  if (a.resid) {
+    if (a.acc_in) epilogue_pipe_t<2, true, true, MULTI>(a, bias_s, rstage, prefix, bar_accfull0, bar_accempty0, tmem, nacc, total_tiles, q, lane, etid);
+    else epilogue_pipe_t<4, true, false, MULTI>(a, bias_s, rstage, prefix, bar_accfull0, bar_accempty0, tmem, nacc, total_tiles, q, lane, etid);
+  } else {
+    if (a.acc_in) epilogue_pipe_t<2, false, true, MULTI>(a, bias_s, rstage, prefix, bar_accfull0, bar_accempty0, tmem, nacc, total_tiles, q, lane, etid);
+    else epilogue_pipe_t<4, false, false, MULTI>(a, bias_s, rstage, prefix, bar_accfull0, bar_accempty0, tmem, nacc, total_tiles, q, lane, etid);
+  }
+}
+
 // ------------------------------------------------------------------------------ the kernel
 // Persistent: grid = min(#tiles, #SMs); every role walks the same static tile sequence
 // w = blockIdx.x, +gridDim.x, ... (tile = 256 rows x n_tile columns of one utterance; column
@@ -778,27 +1028,61 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
 #pragma unroll
       for (int r = 0; r < L; ++r)
         if (rowS + r >= vlo && rowS + r < vhi) smask |= 1u << r;
+      // Channel groups past C_in (C = 24: group 3; C = 48: groups 2-3 of the second chunk) carry zero weights: their
+      // warps skip the arithmetic.  Their z rows are zeroed once so that no stale NaN pattern reaches the MMA.
+      const int live_groups = a.Cin >> 3;
+      if ((NCH - 1) * 4 + kg >= live_groups) {
+        for (int s = 0; s < NZ; ++s) {
+          uint32_t* zk = reinterpret_cast<uint32_t*>(smem + OFF_Z + s * Z_BUF_BYTES) + kg * (ZR * 4) + p;
+#pragma unroll
+          for (int r = 0; r < L; ++r)
+            if ((smask >> r) & 1u) zk[(rowS + r) * 4] = 0u;
+        }
+      }
+      // Shared memory takes all but ~4 KB of the SM's L1, so every global load below is an L2 round trip (0.3-1 us
+      // under load).  The utterance length of the NEXT tile and the snake parameters of the NEXT chunk are therefore
+      // requested one iteration early (ncu: 40 % of the activation warps' stall samples sat on the length load).
       TileCursor cur{prefix};
       int xb = 0, xph = 0, zb = 0, zph = 0;     // ring slot / phase of the next chunk
+      int b = 0, t0 = 0, nt = 0, T = 0;
+      if ((int)blockIdx.x < total_tiles) {
+        cur.locate(blockIdx.x, n_tiles, b, t0, nt);
+        T = a.lengths ? __ldg(a.lengths + b) * a.rate : a.Tmax;
+      }
+      float2 a2n = __ldg(reinterpret_cast<const float2*>(a.a2 + kg * 8 + 2 * p));
+      float2 nhbn = __ldg(reinterpret_cast<const float2*>(a.nhb + kg * 8 + 2 * p));
       for (int w = blockIdx.x; w < total_tiles; w += gridDim.x) {
-        int b, t0, nt;
-        cur.locate(w, n_tiles, b, t0, nt);
-        const int T = a.lengths ? a.lengths[b] * a.rate : a.Tmax;
+        int b2 = 0, t02 = 0, nt2 = 0, T2 = 0;
+        if (w + (int)gridDim.x < total_tiles) {
+          cur.locate(w + gridDim.x, n_tiles, b2, t02, nt2);
+          T2 = a.lengths ? __ldg(a.lengths + b2) * a.rate : a.Tmax;
+        }
         const int m0 = t0 - hc + rowS;
         const int xlo = t0 - X_LEAD;
         // runs whose x window [m0-3, m0+L+2] leaves [0, T) need the replicate clamps (warp-uniform
         // because the run takes part in shuffles)
         const bool edge = __any_sync(0xffffffffu, (m0 - 3 < 0) || (m0 + L + 2 > T - 1));
         for (int c = 0; c < NCH; ++c) {
-          const int ch = c * KC + kg * 8 + 2 * p;
-          const float2 a2v = __ldg(reinterpret_cast<const float2*>(a.a2 + ch));
-          const float2 nhbv = __ldg(reinterpret_cast<const float2*>(a.nhb + ch));
-          k.a2 = pk(a2v.x, a2v.y);
-          k.nhb = pk(nhbv.x, nhbv.y);
-          k.hb = pk(-nhbv.x, -nhbv.y);
-          mbar_wait(BAR_XFULL(xb), xph);
-          mbar_wait(BAR_ZEMPTY(zb), zph ^ 1);
-          if (vlo < ZW) {
+          k.a2 = pk(a2n.x, a2n.y);
+          k.nhb = pk(nhbn.x, nhbn.y);
+          k.hb = pk(-nhbn.x, -nhbn.y);
+          if (NCH > 1) {
+            const int chn = (c + 1 == NCH ? 0 : c + 1) * KC + kg * 8 + 2 * p;
+            a2n = __ldg(reinterpret_cast<const float2*>(a.a2 + chn));
+            nhbn = __ldg(reinterpret_cast<const float2*>(a.nhb + chn));
+          }
+          // warps without work in this chunk (channel groups past C_in, row spans past the z window) still take part in
+          // the ring hand-shakes, but asleep: spinning, they ran NX chunks ahead and then burnt 10-20 % of the SM's
+          // issue slots on try_wait loops (ncu: 750-1900 polls per tile on the C = 24 layers)
+          const bool live = vlo < ZW && c * 4 + kg < live_groups;
+          if (live) {
+            mbar_wait(BAR_XFULL(xb), xph);
+            mbar_wait(BAR_ZEMPTY(zb), zph ^ 1);
+          } else {
+            mbar_wait_relaxed(BAR_XFULL(xb), xph, 1000);
+            mbar_wait_relaxed(BAR_ZEMPTY(zb), zph ^ 1, 1000);
+          }
+          if (live) {
             const uint32_t* xk = reinterpret_cast<const uint32_t*>(smem + OFF_X + xb * X_BUF_BYTES) + kg * (XRA * 4) + p;
             uint32_t* zk = reinterpret_cast<uint32_t*>(smem + OFF_Z + zb * Z_BUF_BYTES) + kg * (ZR * 4) + p;
             if (t0 - hc + vlo >= T) {
@@ -821,6 +1105,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
           if (++xb == NX) { xb = 0; xph ^= 1; }
           if (++zb == NZ) { zb = 0; zph ^= 1; }
         }
+        b = b2; t0 = t02; nt = nt2; T = T2;
       }
     }
   } else if (warp < NW_ACT + 4) {
@@ -834,14 +1119,17 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
           int b, t0, nt;
           cur.locate(w, n_tiles, b, t0, nt);
           for (int c = 0; c < NCH; ++c) {
-            mbar_wait_relaxed(BAR_XEMPTY(xb), xph ^ 1, 500);
-            mbar_expect_tx(BAR_XFULL(xb), X_TX_BYTES);
+            mbar_wait_relaxed(BAR_XEMPTY(xb), xph ^ 1, 200);
+            // activated layers never read the channel groups past C_in (their warps skip); plain convs feed the
+            // x tile to the MMA as it is and need the TMA zero fill of those groups
+            const int lg = ACT ? min(4, (a.Cin >> 3) - c * 4) : 4;
+            mbar_expect_tx(BAR_XFULL(xb), (uint32_t)lg * (X_TX_BYTES / 4));
             const uint32_t dst = s_base + OFF_X + xb * X_BUF_BYTES;
 #pragma unroll
             for (int kg = 0; kg < 4; ++kg)
 #pragma unroll
               for (int h = 0; h < 2; ++h)
-                tma_load_4d(dst + kg * (XRA * 16) + h * (BOXR * 16), &tmx, 0, t0 - X_LEAD + h * BOXR, c * 4 + kg, b,
+                if (kg < lg) tma_load_4d(dst + kg * (XRA * 16) + h * (BOXR * 16), &tmx, 0, t0 - X_LEAD + h * BOXR, c * 4 + kg, b,
                             BAR_XFULL(xb));
             if (++xb == NX) { xb = 0; xph ^= 1; }
           }
@@ -868,6 +1156,10 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
       }
     } else if (warp == NW_ACT + 2) {
       // ===================== MMA issuer =====================
+      // One thread, 32 registers: everything loop-carried is kept to a minimum (one operand ring index instead of
+      // separate x / z cursors, descriptors rebuilt from 32-bit address units) because a spilled value costs an L2
+      // round trip here — shared memory leaves the SM ~4 KB of L1 — and this thread is the serial link between the
+      // activation warps and the epilogue.
       if (lane == 0) {
         const uint32_t idesc = make_idesc_bf16(128, n_tile);
         const uint32_t lboA = (ACT ? ZR : XRA) * 16;
@@ -876,21 +1168,24 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
         // move the 14-bit address field (rows are 16 B apart: +1 unit = +1 time sample)
         const u64 hiA = make_sdesc(0, lboA, 128), hiB = make_sdesc(0, lboB, 128);
         const uint32_t ksA = 2 * lboA / 16, ksB = 2 * lboB / 16, tileU = (uint32_t)tile_bytes / 16;
-        int stage = 0, phase = 0, it = 0;
-        int xb = 0, xph = 0, zb = 0, zph = 0;
+        const int ND = ACT ? NZ : NX;                       // depth of the A-operand ring (z tiles, or raw x tiles)
+        const uint32_t ring0 = (ACT ? (s_base + OFF_Z) : (s_base + OFF_X + (X_LEAD - a.lead) * 16)) >> 4;
+        const uint32_t ringU = (ACT ? Z_BUF_BYTES : X_BUF_BYTES) >> 4;
+        const uint32_t barF = ACT ? BAR_ZFULL(0) : BAR_XFULL(0), barE = ACT ? BAR_ZEMPTY(0) : BAR_XEMPTY(0);
+        const bool lazy = ACT && a.Cin <= 96 && !(a.dbg & 4);
+        int stage = 0, phase = 0, rb = 0, rph = 0, it = 0;
         for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++it) {
           const int as = (nacc == 2) ? (it & 1) : 0;
-          const int ause = (nacc == 2) ? (it >> 1) : it;
-          mbar_wait(BAR_ACCEMPTY(as), (ause & 1) ^ 1);        // epilogue has drained this stage
+          mbar_wait(BAR_ACCEMPTY(as), ((((nacc == 2) ? (it >> 1) : it) & 1) ^ 1));   // epilogue has drained this stage
           tc_fence_after();
           const uint32_t tm = tmem + (uint32_t)(as * 2 * n_tile);
           uint32_t accflag = 0;
           for (int c = 0; c < NCH; ++c) {
-            if (ACT) mbar_wait(BAR_ZFULL(zb), zph);
-            else mbar_wait(BAR_XFULL(xb), xph);
+            // narrow layers are bound by the activation warps' issue slots: the issuer sleeps between polls there
+            if (lazy) mbar_wait_relaxed(barF + 8 * rb, rph, 64);
+            else mbar_wait(barF + 8 * rb, rph);
             tc_fence_after();
-            const uint32_t aU = (ACT ? (s_base + OFF_Z + zb * Z_BUF_BYTES)
-                                     : (s_base + OFF_X + xb * X_BUF_BYTES + (X_LEAD - a.lead) * 16)) >> 4;
+            const uint32_t aU = ring0 + (uint32_t)rb * ringU;
             for (int s = 0; s < spc; ++s) {
               const int taps = min(tps, a.K - s * tps);
               mbar_wait(BAR_WFULL(stage), phase);
@@ -910,9 +1205,8 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
               umma_commit(BAR_WEMPTY(stage));          // weight stage free once these MMAs retire
               if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
             }
-            umma_commit(ACT ? BAR_ZEMPTY(zb) : BAR_XEMPTY(xb));
-            if (++xb == NX) { xb = 0; xph ^= 1; }
-            if (++zb == NZ) { zb = 0; zph ^= 1; }
+            umma_commit(barE + 8 * rb);
+            if (++rb == ND) { rb = 0; rph ^= 1; }
           }
           umma_commit(BAR_ACCFULL(as));
         }
@@ -921,10 +1215,16 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
   } else {
     // ===================== epilogue warps: TMEM -> (+bias, +resid, +sum, /div) -> bf16 -> HBM ====
     reg_dec<64>();
-    if (a.up == 0 && n_tiles == 1 && !(a.dbg & 1024))   // conv mode: the lean packed-math epilogue
+    if (a.up == 0 && n_tiles == 1 && !(a.dbg & 1024))   // conv mode: the pipelined packed-math epilogue
+      epilogue_pipe<false>(a, bias_s, smem + off_r(NX, NZ, W_STAGES), prefix, BAR_ACCFULL(0), BAR_ACCEMPTY(0), tmem, nacc, total_tiles, warp & 3, lane,
+                           threadIdx.x - (NW_ACT + 4) * 32);
+    else if (a.up == 0 && !(a.dbg & 1024))
+      epilogue_pipe<true>(a, bias_s, smem + off_r(NX, NZ, W_STAGES), prefix, BAR_ACCFULL(0), BAR_ACCEMPTY(0), tmem, nacc, total_tiles, warp & 3, lane,
+                          threadIdx.x - (NW_ACT + 4) * 32);
+    else if (a.up == 0 && n_tiles == 1)
       epilogue_fir<16, false>(a, bias_s, prefix, BAR_ACCFULL(0), BAR_ACCEMPTY(0), tmem, nacc, total_tiles, warp & 3, lane,
                               threadIdx.x - (NW_ACT + 4) * 32);
-    else if (a.up == 0 && !(a.dbg & 1024))
+    else if (a.up == 0)
       epilogue_fir<16, true>(a, bias_s, prefix, BAR_ACCFULL(0), BAR_ACCEMPTY(0), tmem, nacc, total_tiles, warp & 3, lane,
                              threadIdx.x - (NW_ACT + 4) * 32);
     else

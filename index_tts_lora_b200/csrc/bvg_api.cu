@@ -2,6 +2,8 @@
 // orchestration of the fp32 SIMT path, per-op entry points.  The bf16 tcgen05 path lives in
 // decode_tc.cu and is dispatched from here.
 #include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -675,14 +677,20 @@ int bvg_plan_set_profiling(bvg_plan* p, int enable) {
 }
 
 int bvg_set_tc_fir_max_channels(int max_c) { return bvg::tc_set_fir_max_c(max_c); }
+int bvg_set_tc_split_min_channels(int min_c) { return bvg::tc_set_split_min_c(min_c); }
 
 int bvg_plan_read_profile(bvg_plan* p, bvg_profile* out) {
   BVG_REQUIRE(p && out, "bvg_plan_read_profile: null argument");
   BVG_CUDA(cudaSetDevice(p->device));
+  static const bool dump = getenv("BVG_PROF_DUMP") != nullptr;   // per-launch lines on stderr (tools/)
+  int idx = 0;
   for (const ProfRec& r : p->prof) {
     BVG_CUDA(cudaEventSynchronize(r.e1));
     float ms = 0.f;
     BVG_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    if (dump)
+      fprintf(stderr, "bvg_prof %d cls %d us %.1f gflop %.2f mbytes %.1f\n", idx++, r.cls, ms * 1e3, r.flops * 1e-9,
+              r.bytes * 1e-6);
     p->prof_acc.ms[r.cls] += ms;
     p->prof_acc.flops[r.cls] += r.flops;
     p->prof_acc.bytes[r.cls] += r.bytes;

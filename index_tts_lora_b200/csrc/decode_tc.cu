@@ -2,6 +2,7 @@
 // launch selection and the decode orchestration (models.py:212-252) on the blocked bf16 layout.
 #include <cuda.h>
 
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -9,12 +10,15 @@
 #include <tuple>
 #include <vector>
 
+#include "act_blk.cuh"
 #include "amp_fir.cuh"
 #include "amp_tc.cuh"
 #include "tc_api.h"
 
 namespace bvg {
 using namespace tc;
+
+constexpr int kSplitMinCDefault = 0;   // see split_layer()
 
 // ------------------------------------------------------------------------------ small kernels
 // folded fp32 tap-major weights [Cin][K][Cout] -> bf16 UMMA tiles [ntile][chunk][tap][4][n_tile][8]
@@ -123,6 +127,8 @@ struct TcPlan {
   // the 3 AMP blocks of a stage are independent given xin (models.py:239-244): they run on three
   // streams (caller's + 2 owned) so their persistent grids back-fill each other's tails
   void* cbuf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  void* zbuf[3] = {nullptr, nullptr, nullptr};   // Activation1d output of the split layers (one per block stream)
+  size_t zbuf_bytes = 0;
   size_t cbuf_bytes = 0;
   cudaStream_t aux[2] = {nullptr, nullptr};
   void* shard = nullptr;            // ShardState (time-split P2P decode)
@@ -227,6 +233,7 @@ void tc_plan_free(bvg_plan* p) {
   for (void* q : t->owned) cudaFree(q);
   if (t->lat_blk) cudaFree(t->lat_blk);
   for (void* q : t->cbuf) if (q) cudaFree(q);
+  for (void* q : t->zbuf) if (q) cudaFree(q);
   for (cudaStream_t q : t->aux) if (q) cudaStreamDestroy(q);
   if (t->ev_fork) cudaEventDestroy(t->ev_fork);
   for (cudaEvent_t e : t->ev_last) if (e) cudaEventDestroy(e);
@@ -237,7 +244,7 @@ void tc_plan_free(bvg_plan* p) {
 int64_t tc_plan_workspace_bytes(const bvg_plan* p) {
   if (!p->tc) return 0;
   const TcPlan* t = static_cast<const TcPlan*>(p->tc);
-  return (int64_t)(t->lat_bytes + 6 * t->cbuf_bytes);
+  return (int64_t)(t->lat_bytes + 6 * t->cbuf_bytes + 3 * t->zbuf_bytes);
 }
 
 // ------------------------------------------------------------------------------ tensor maps
@@ -308,6 +315,7 @@ struct TcLaunch {
   int up = 0, pad = 0, cphase = 0;   // ConvTranspose1d mode
   int out_tstride = 0;               // defaults to Tstride
   int st_lo = 0, st_hi = 0x7fffffff; // store range (rows) of a conv-mode launch
+  __nv_bfloat16* zbuf = nullptr;     // scratch for the split form (act_blk.cuh), same geometry as x
 };
 
 template <int L, bool ACT>
@@ -320,6 +328,14 @@ static int launch_inst(const CUtensorMap& map, const TcArgs& a, dim3 grid, cudaS
   }
   const int smem = smem_bytes(a.nx, a.nz, a.wst);
   if (smem > 227 * 1024) return fail(BVG_ERR_STATE, "k_amp_tc smem plan %d B exceeds 227 KB", smem);
+  // Whatever the rings leave of the 228 KB goes to L1, which is what serves the register spills of the 32- / 64-register
+  // roles (local memory) and the few global scalars: ask for the smallest carve-out that holds this launch.
+  static int carve = -1;
+  const int want = std::min(100, (smem + 1024) * 100 / (228 * 1024) + 1);
+  if (want != carve) {
+    BVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, want));
+    carve = want;
+  }
   kern<<<grid, NTHREADS, smem, st>>>(map, a);
   BVG_CUDA(cudaGetLastError());
   return 0;
@@ -353,8 +369,65 @@ static int fir_max_c() {
   return g_fir_max_c;
 }
 
+// Layers with C_in >= this many channels run Activation1d once in k_act_blk and the conv as k_amp_tc<ACT = false>
+// (act_blk.cuh) instead of repeating the activation per column tile inside the fused kernel.  0 = never.
+static int g_split_min_c = -1;
+int tc_set_split_min_c(int v) {
+  const int old = g_split_min_c < 0 ? kSplitMinCDefault : g_split_min_c;
+  g_split_min_c = v < 0 ? 0 : v;
+  return old;
+}
+static int split_min_c() {
+  if (g_split_min_c < 0) {
+    const char* e = getenv("BVG_SPLIT_MIN_C");
+    g_split_min_c = e ? atoi(e) : kSplitMinCDefault;
+  }
+  return g_split_min_c;
+}
+static bool split_layer(int Cin) { return split_min_c() > 0 && Cin >= split_min_c(); }
+
+static int launch_act_blk(bvg_plan* p, const ConvW& cw, const ActW* aw, const TcLayer& L, const TcLaunch& q,
+                          cudaStream_t st) {
+  AbArgs b{};
+  b.x = static_cast<const __nv_bfloat16*>(q.x); b.z = q.zbuf; b.a2 = L.a2; b.nhb = L.nhb; b.lengths = q.d_len;
+  b.B = q.B; b.groups = cw.Cin / 8; b.Tstride = q.Tstride; b.rate = q.rate; b.Tmax = q.Tstride;
+  b.nslices = (q.Tstride + AB_V - 1) / AB_V;
+  for (int i = 0; i < 12; ++i) { b.up2[i] = 2.0f * aw->up[i]; b.dn[i] = aw->dn[i]; }
+  const long long units = (long long)b.B * b.groups * b.nslices;
+  if (units >= (1LL << 31)) return fail(BVG_ERR_UNSUPPORTED, "k_act_blk: %lld work units exceed 2^31", units);
+  const int sms = q.sm_count > 0 ? q.sm_count : 148;
+  const int smem = AB_WARPS * AB_SMEM_PER_WARP + 8192;   // tail slack: the edge path's clamped reads of unused rows
+  static bool attr = false;
+  if (!attr) {
+    BVG_CUDA(cudaFuncSetAttribute(k_act_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  dim3 grid((unsigned)std::min<long long>((units + AB_WARPS - 1) / AB_WARPS, 2LL * sms));
+  const double samples = (p ? p->cur_sum_frames : 0.0) * q.rate;
+  prof_begin(p, st, q.cls, 0.0, samples * 2.0 * 2.0 * cw.Cin);
+  k_act_blk<<<grid, AB_WARPS * 32, smem, st>>>(b);
+  prof_end(p, st);
+  BVG_CUDA(cudaGetLastError());
+  if (p) ++p->last_launches;
+  return 0;
+}
+
 static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, const ConvW& cw, const ActW* aw,
                      const TcLaunch& q, cudaStream_t st) {
+  if (aw && !q.up && q.zbuf && split_layer(cw.Cin)) {
+    // split form: z = Activation1d(x) once, then the plain dilated conv over z
+    int rc;
+    if ((rc = launch_act_blk(p, cw, aw, L, q, st))) return rc;
+    CUtensorMap tmp;
+    const CUtensorMap* zm = &tmp;
+    TcPlan* t = p ? static_cast<TcPlan*>(p->tc) : nullptr;
+    if (t) rc = get_map(t, q.zbuf, cw.Cin, q.Tstride, q.B, &zm);
+    else rc = make_map(q.zbuf, cw.Cin, q.Tstride, q.B, &tmp);
+    if (rc) return rc;
+    TcLaunch qc = q;
+    qc.x = q.zbuf; qc.zbuf = nullptr;
+    return launch_tc(p, *zm, L, cw, nullptr, qc, st);
+  }
   TcArgs a{};
   a.wt = L.wt; a.bias = cw.bias; a.bias_b = q.bias_b; a.bias_b_stride = q.bias_b_stride;
   a.resid = q.resid; a.acc_in = q.acc_in; a.out = q.out; a.div = q.div;
@@ -363,7 +436,18 @@ static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, cons
   // ring depths.  Timing experiments (BVG_DBG) showed the weight stream is not the limiter (no change with
   // 16-byte copies) while the single TMEM accumulator stage of the wide layers (4*n_tile > 512) stalls the
   // MMAs of the next tile during the epilogue; 4 z buffers let the activation warps run ahead meanwhile.
-  a.nx = 3; a.nz = 4; a.wst = 4;
+  // ring depths (22 / 21.5 / 16 KB per slot; 32 KB go to the epilogue's residual staging).  Narrow layers stream x
+  // tile after tile (one chunk per tile) and need little weight staging; wide layers walk 6-24 chunks per tile.
+  if (cw.Cin <= 96 && !q.up) { a.nx = 3; a.nz = 3; a.wst = 3; }
+  else { a.nx = 2; a.nz = 3; a.wst = 4; }
+  {
+    static int ov[3] = {-1, -1, -1};      // BVG_RINGS="nx,nz,wst": experiment hook
+    if (ov[0] < 0) {
+      ov[0] = 0;
+      if (const char* e = getenv("BVG_RINGS")) sscanf(e, "%d,%d,%d", &ov[0], &ov[1], &ov[2]);
+    }
+    if (ov[0] > 0) { a.nx = ov[0]; a.nz = ov[1]; a.wst = ov[2]; }
+  }
   a.Tstride = q.out_tstride ? q.out_tstride : q.Tstride;
   a.lengths = q.d_len; a.rate = q.rate; a.Tmax = q.Tstride;
   a.up = q.up; a.pad = q.pad; a.cphase = q.cphase;
@@ -458,6 +542,19 @@ static int tc_prepare(bvg_plan* p, TcPlan* t, int B, int Fs) {
     t->cbuf_bytes = buf_bytes;
     t->maps.clear();
   }
+  // scratch of the split layers: the largest split stage (channels x rows), one buffer per block stream
+  size_t z_elems = 0;
+  for (int i = 0; i < p->n_stages; ++i)
+    if (split_layer(p->C[i + 1])) z_elems = std::max(z_elems, (size_t)p->C[i + 1] * Fs * p->rate[i + 1]);
+  const size_t z_bytes = z_elems * B * sizeof(__nv_bfloat16);
+  if (z_bytes > t->zbuf_bytes) {
+    BVG_CUDA(cudaDeviceSynchronize());
+    for (void*& qb : t->zbuf) { if (qb) BVG_CUDA(cudaFree(qb)); qb = nullptr; }
+    t->zbuf_bytes = 0;
+    for (void*& qb : t->zbuf) BVG_CUDA(cudaMalloc(&qb, z_bytes));
+    t->zbuf_bytes = z_bytes;
+    t->maps.clear();
+  }
   if (!t->ev_fork) {
     for (cudaStream_t& q : t->aux) BVG_CUDA(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
     BVG_CUDA(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
@@ -526,6 +623,7 @@ static int tc_stage(bvg_plan* p, TcPlan* t, int i, const StageIO& io, cudaStream
       TcLaunch qa;
       qa.x = xcur; qa.out = xt; qa.dil = d; qa.B = B; qa.Tstride = Ti; qa.rate = Ri; qa.d_len = io.d_len; qa.cls = cls;
       qa.h_len = io.h_len; qa.sm_count = p->sm_count;
+      qa.zbuf = split_layer(Ci) ? (__nv_bfloat16*)t->zbuf[j % 3] : nullptr;
       if ((rc = get_map(t, xcur, Ci, Ti, B, &map))) return rc;
       if ((rc = launch_tc(p, *map, t->rb1[n][m], p->rb1[n][m], &p->rba[n][2 * m], qa, sq))) return rc;
 
@@ -533,6 +631,7 @@ static int tc_stage(bvg_plan* p, TcPlan* t, int i, const StageIO& io, cudaStream
       TcLaunch qb;
       qb.x = xt; qb.resid = xcur; qb.dil = 1; qb.B = B; qb.Tstride = Ti; qb.rate = Ri; qb.d_len = io.d_len; qb.cls = cls;
       qb.h_len = io.h_len; qb.sm_count = p->sm_count;
+      qb.zbuf = qa.zbuf;
       if (!last) {
         qb.out = xr;
       } else {
@@ -841,11 +940,12 @@ int tc_amp_layer(const float* x, float* y, const float* resid, int B, int C_in, 
   ConvW cw; ActW aw;
   cw.Cin = C_in; cw.Cout = C_out; cw.K = k;
   const size_t nw = (size_t)C_out * C_in * k;
-  __nv_bfloat16 *xb, *yb, *rb = nullptr;
+  __nv_bfloat16 *xb, *yb, *rb = nullptr, *zb = nullptr;
   float *a_dev = nullptr, *invb_dev = nullptr;
   if (alloc((void**)&cw.wp, nw * 4) || alloc((void**)&xb, (size_t)B * C_in * T * 2) ||
       alloc((void**)&yb, (size_t)B * C_out * T * 2) || alloc((void**)&a_dev, C_in * 4) || alloc((void**)&invb_dev, C_in * 4) ||
-      (resid && alloc((void**)&rb, (size_t)B * C_out * T * 2))) {
+      (resid && alloc((void**)&rb, (size_t)B * C_out * T * 2)) ||
+      (act && split_layer(C_in) && alloc((void**)&zb, (size_t)B * C_in * T * 2))) {
     cleanup();
     return fail(BVG_ERR_CUDA, "tc_amp_layer: allocation failed");
   }
@@ -873,6 +973,7 @@ int tc_amp_layer(const float* x, float* y, const float* resid, int B, int C_in, 
   if ((rc = make_map(xb, C_in, T, B, &map))) { cleanup(); return rc; }
   TcLaunch q;
   q.x = xb; q.resid = rb; q.out = yb; q.dil = dilation; q.B = B; q.Tstride = T; q.rate = 1; q.d_len = nullptr;
+  q.zbuf = zb;
   {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);

@@ -13,6 +13,7 @@ int tc_amp_layer(const float* x, float* y, const float* resid, int B, int C_in, 
                  const float* up_filter, const float* down_filter, const float* alpha,
                  const float* beta, int logscale, cudaStream_t st);
 int tc_set_fir_max_c(int v);
+int tc_set_split_min_c(int v);
 // time-split P2P decode (decode_tc.cu)
 int tc_shard_setup(bvg_plan* p, const bvg_shard_geom* g, cudaStream_t st);
 int tc_shard_halo_frames(bvg_plan* p);

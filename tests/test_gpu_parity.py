@@ -417,3 +417,84 @@ def test_full_generator_bf16_tensor_core_fir_snr():
     snr = _snr(ref, wav)
     print("bf16 + tensor-core FIR SNR dB", snr)
     assert snr > BF16_SNR_DB, snr
+
+
+# ============================================================================= split form (act_blk.cuh)
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,d", [(3, 1), (7, 3), (11, 5)])
+@pytest.mark.parametrize("C,T", [(24, 700), (48, 1500), (96, 5), (24, 3), (384, 257), (768, 70)])
+def test_amp_layer_bf16_split_equals_fused(k, d, C, T):
+    """Split form of an AMP layer (Activation1d once in k_act_blk -> scratch -> k_amp_tc<ACT=false>) against the
+    fused kernel: the z rows come from the same act_run<> code and feed the same MMA sequence, so the outputs
+    must be bit-identical — including the sequence-edge rows (T = 3, 5) and the partial last unit / tile."""
+    from index_tts_lora_b200.models import AMPBlock1
+    from index_tts_lora_b200.ops import amp_layer
+    from index_tts_lora_b200 import synth, _lib
+    from index_tts_lora_b200.config import AttrDict
+    O = _oracle()
+    dev = _dev()
+    lib = _lib.load()
+    blk = AMPBlock1(AttrDict(snake_logscale=True), C, k, (d, d, d), activation="snakebeta")
+    sd = synth.synth_state_dict(blk.state_dict(), seed=k * 100 + d, profile="stress")
+    blk.load_state_dict(sd)
+    x = torch.randn(2, C, T, generator=synth._gen(1, f"x{C}{T}"))
+    r = torch.randn(2, C, T, generator=synth._gen(2, f"r{C}{T}"))
+    ref = O.amp_layer(x, sd, "activations.0", "convs1.0", k, d) + r
+    old = lib.bvg_set_tc_split_min_channels(0)
+    try:
+        y_fused = amp_layer(x.to(dev), blk.convs1[0], blk.activations[0], resid=r.to(dev), precision="bf16").cpu()
+        lib.bvg_set_tc_split_min_channels(8)
+        y_split = amp_layer(x.to(dev), blk.convs1[0], blk.activations[0], resid=r.to(dev), precision="bf16").cpu()
+    finally:
+        lib.bvg_set_tc_split_min_channels(old)
+    assert _snr(ref, y_split) > 35.0, _snr(ref, y_split)
+    assert torch.equal(y_fused, y_split), (y_fused - y_split).abs().max().item()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("min_c", [8, 192])
+def test_ragged_batch_bf16_split_equals_fused(min_c):
+    """Whole decode of a mixed-length batch: every layer (min_c = 8) or only the wide stages in split form equals
+    the all-fused decode bit for bit; rows past each utterance's end stay zero."""
+    from index_tts_lora_b200.config import default_config
+    from index_tts_lora_b200 import synth, _lib
+    from index_tts_lora_b200.models import BigVGAN
+    dev = _dev()
+    lib = _lib.load()
+    h = default_config()
+    m = BigVGAN(h)
+    m.load_state_dict(synth.synth_state_dict(m.state_dict(), seed=1234, profile="stress"))
+    m = m.to(dev).eval()
+    m.precision = "bf16"
+    lengths = [23, 7, 1, 40]
+    lat = synth.synth_latent(len(lengths), max(lengths), h.gpt_dim, seed=3).to(dev)
+    emb = m.speaker_embedding(synth.synth_mel(1, 120, h.num_mels, seed=4).to(dev)).expand(len(lengths), -1, -1)
+    old = lib.bvg_set_tc_split_min_channels(0)
+    try:
+        fused = m.decode(lat, emb, lengths=lengths, out_dtype=torch.float32).cpu()
+        lib.bvg_set_tc_split_min_channels(min_c)
+        split = m.decode(lat, emb, lengths=lengths, out_dtype=torch.float32).cpu()
+        split2 = m.decode(lat, emb, lengths=lengths, out_dtype=torch.float32).cpu()
+    finally:
+        lib.bvg_set_tc_split_min_channels(old)
+    assert torch.equal(split, split2)
+    assert torch.equal(fused, split), (fused - split).abs().max().item()
+    for b, L in enumerate(lengths):
+        if L < max(lengths):
+            assert split[b, :, L * 1024:].abs().max().item() == 0.0
+
+
+@pytest.mark.gpu
+def test_full_generator_bf16_split_snr():
+    """BASELINE config 2 on the split form for every layer: SNR >= 40 dB against the reference's fp32 output."""
+    from index_tts_lora_b200.config import default_config
+    from index_tts_lora_b200 import _lib
+    lib = _lib.load()
+    old = lib.bvg_set_tc_split_min_channels(8)
+    try:
+        wav, ref, *_ = _run_case("full_f157_init", default_config(), "bf16")
+    finally:
+        lib.bvg_set_tc_split_min_channels(old)
+    snr = _snr(ref, wav)
+    print("bf16 split form SNR dB", snr)
+    assert snr > BF16_SNR_DB, snr
