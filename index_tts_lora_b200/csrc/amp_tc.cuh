@@ -52,13 +52,17 @@ constexpr int Z_BUF_BYTES = 4 * ZR * 16;   // 21504
 constexpr int OFF_BIAS = 0;
 constexpr int OFF_PREFIX = OFF_BIAS + 2 * 256 * 4;
 constexpr int OFF_BAR = OFF_PREFIX + (MAX_B + 8) * 4;
-constexpr int NUM_BARS = 2 * NX_MAX + 2 * NZ_MAX + 2 * W_STAGES_MAX + 4;
+constexpr int NUM_BARS = 2 * NX_MAX + 2 * NZ_MAX + 2 * W_STAGES_MAX + 4 + 4;   // + residual ring full / empty x 2
 constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
 constexpr int OFF_X = (OFF_TMEM + 16 + 127) / 128 * 128;
 __host__ __device__ constexpr int off_z(int nx) { return OFF_X + nx * X_BUF_BYTES; }
 __host__ __device__ constexpr int off_w(int nx, int nz) { return off_z(nx) + nz * Z_BUF_BYTES; }
 constexpr int R_SLOTS = 16;                       // 16-byte rows per epilogue thread staged for the residual / running sum
 constexpr int R_STAGE_BYTES = R_SLOTS * 128 * 16; // 32 KB: [slot][epilogue thread][16 B]
+// ... or, when the residual is added by the tensor core, two slots of [4 channel groups][256 rows][16 B] (UMMA A layout)
+constexpr int R_RING = 2;
+constexpr int R_SLOT_BYTES = 4 * M_TILE * 16;     // 16 KB
+static_assert(R_RING * R_SLOT_BYTES == R_STAGE_BYTES, "the two uses share one region");
 __host__ __device__ constexpr int off_r(int nx, int nz, int wst) { return off_w(nx, nz) + wst * W_STAGE_BYTES; }
 __host__ __device__ constexpr int smem_bytes(int nx, int nz, int wst) { return off_r(nx, nz, wst) + R_STAGE_BYTES; }
 
@@ -75,6 +79,10 @@ struct TcArgs {
   int nx, nz, wst;             // ring depths: x buffers (2..3), z buffers (2..4), weight stages (<= 8)
   const __nv_bfloat16* xin;    // k_amp_fir: the blocked input buffer itself (interior boxes are plain 1-D bulk copies)
   int xgroups;                 // channel groups of xin
+  // residual / running-sum add on the tensor core (D += R x I): identity weight tiles [ntile][chunk][1][4][n_tile][8],
+  // chunks of 32 channels per column tile, and which streams are on (their rows arrive through tmr / tmq)
+  const __nv_bfloat16* idw;
+  int nchr, rmma_r, rmma_q;
   int dbg;                     // timing experiments only (BVG_DBG env): 1 = 1 of 4 MMAs per tap, 2 = 16-byte weight copies
   int st_lo, st_hi;            // conv mode: only rows in [st_lo, st_hi) are stored (time-split shards keep
                                // their hands off the halo rows that the neighbouring GPUs write)
@@ -116,14 +124,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // Polite wait for the roles that are normally far ahead of the activation warps (producers,
 // epilogue): poll, then sleep `ns` so the polling does not eat the activation warps' issue slots.
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t ns) {
+  // try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or the hint expires,
+  // so a long wait costs a handful of instructions instead of a poll every few dozen cycles (nanosleep with small
+  // arguments was measured to return after ~20 ns: ~440 polls per tile from the three single-thread roles)
   uint32_t done;
+  const uint32_t hint = ns * 20u;
   for (;;) {
     asm volatile(
         "{\n\t.reg .pred P1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, P1;\n\t}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t}\n" : "=r"(done) : "r"(bar), "r"(parity), "r"(hint) : "memory");
     if (done) break;
-    asm volatile("nanosleep.u32 %0;" ::"r"(ns));
   }
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
@@ -799,29 +810,12 @@ __device__ __forceinline__ void epilogue_pipe_t(const TcArgs& a, float* bias_s, 
   TileCursor cur{prefix};
   int it = 0, last_b = -1, last_nt = -1;
   int T_next = 0;                      // length of the next tile's utterance, requested one tile early (L2 round trip)
-  // L2 prefetch of one tile's residual / running-sum rows (this thread's two rows, all live column groups)
-  auto prefetch_tile = [&](int w) {
-    if (w >= total_tiles) return;
+  auto prefetch_tile = [&](int w) {     // only the utterance length is fetched ahead (an L2 prefetch of the rows
+    if (w >= total_tiles) return;       // themselves was measured to cost more than it saves once they are staged)
     TileCursor c2 = cur;
     int b, t0, nt;
     c2.locate(w, n_tiles, b, t0, nt);
     T_next = a.lengths ? __ldg(a.lengths + b) * a.rate : a.Tmax;
-    if (!(HAS_R || HAS_Q) || (a.dbg & 128)) return;
-    if (!MULTI) nt = 0;
-    const int cgn0 = nt * (n_tile >> 3);
-    const int ng = min(n_tile >> 3, cg_total - cgn0);
-    const size_t ubase = ((size_t)b * cg_total + cgn0) * a.Tstride * 8;
-#pragma unroll 1
-    for (int mb = 0; mb < 2; ++mb) {
-      const int t = t0 + mb * 128 + q * 32 + lane;
-      if (t >= a.Tmax) continue;       // rows past the utterance's end are inside the buffer: no need to wait for T_next
-      size_t o = ubase + (size_t)t * 8;
-#pragma unroll 1
-      for (int g = 0; g < ng; ++g, o += gstride) {
-        if constexpr (HAS_R) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.resid + o));
-        if constexpr (HAS_Q) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.acc_in + o));
-      }
-    }
   };
   prefetch_tile(blockIdx.x);
   for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++it) {
@@ -942,9 +936,10 @@ template <int REGS>
 __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
 
 
-template <int L, bool ACT>
+template <int L, bool ACT, bool RM>
 __global__ void __launch_bounds__(NTHREADS, 1)
-k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs a) {
+k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmr,
+         const __grid_constant__ CUtensorMap tmq, const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tile = a.n_tile, n_tiles = a.n_tiles;
@@ -961,6 +956,10 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
   auto BAR_WEMPTY = [&](int i) { return bar0 + 8 * (2 * NX_MAX + 2 * NZ_MAX + W_STAGES_MAX + i); };
   auto BAR_ACCFULL = [&](int i) { return bar0 + 8 * (2 * NX_MAX + 2 * NZ_MAX + 2 * W_STAGES_MAX + i); };
   auto BAR_ACCEMPTY = [&](int i) { return bar0 + 8 * (2 * NX_MAX + 2 * NZ_MAX + 2 * W_STAGES_MAX + 2 + i); };
+  auto BAR_RFULL = [&](int i) { return bar0 + 8 * (2 * NX_MAX + 2 * NZ_MAX + 2 * W_STAGES_MAX + 4 + i); };
+  auto BAR_REMPTY = [&](int i) { return bar0 + 8 * (2 * NX_MAX + 2 * NZ_MAX + 2 * W_STAGES_MAX + 6 + i); };
+  const int OFF_R = off_r(NX, NZ, W_STAGES);
+  const int nstreams_r = RM ? (a.rmma_r ? 1 : 0) + (a.rmma_q ? 1 : 0) : 0;   // residual-like streams added by identity MMAs
   float* bias_s = reinterpret_cast<float*>(smem + OFF_BIAS);
   int* prefix = reinterpret_cast<int*>(smem + OFF_PREFIX);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM);
@@ -997,6 +996,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
     for (int i = 0; i < NX_MAX; ++i) { mbar_init(BAR_XFULL(i), 1); mbar_init(BAR_XEMPTY(i), ACT ? NW_ACT : 1); }
     for (int i = 0; i < NZ_MAX; ++i) { mbar_init(BAR_ZFULL(i), NW_ACT); mbar_init(BAR_ZEMPTY(i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(BAR_ACCFULL(i), 1); mbar_init(BAR_ACCEMPTY(i), 4); }
+    for (int i = 0; i < R_RING; ++i) { mbar_init(BAR_RFULL(i), 1); mbar_init(BAR_REMPTY(i), 1); }
     for (int i = 0; i < W_STAGES_MAX; ++i) { mbar_init(BAR_WFULL(i), 1); mbar_init(BAR_WEMPTY(i), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmx)) : "memory");
@@ -1020,7 +1020,14 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
       load_taps(k, a);
       // 4 channel groups x 4 warps; a warp's 8 runs of L rows span 8L rows and yield V = 8L-6 z rows
       constexpr int V = 8 * L - 6;
-      const int kg = warp & 3, wq = warp >> 2, g = lane >> 2, p = lane & 3;
+      // warp -> (channel group kg, time quarter wq).  Warps w, w+4, w+8, w+12 share one SM sub-partition (scheduler
+      // = warp % 4): they take the four channel groups of ONE time quarter, so that the groups past C_in (C = 24: kg 3;
+      // C = 48, second chunk: kg 2-3), whose warps idle, are spread over all four schedulers instead of leaving one
+      // scheduler empty and the other three issue-bound.
+      // Measured: with no idle groups (C a multiple of 32) the transposed assignment is the faster one by ~5 %.
+      const bool spread = (a.dbg & 256) ? false : ((a.dbg & 512) ? true : (a.Cin & 31) != 0);
+      const int kg = spread ? (warp >> 2) : (warp & 3), wq = spread ? (warp & 3) : (warp >> 2);
+      const int g = lane >> 2, p = lane & 3;
       const int ZW = M_TILE + 2 * hc;
       const int vlo = wq * V, vhi = min(vlo + V, ZR);
       const int rowS = vlo - 3 + g * L;
@@ -1137,12 +1144,17 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
       }
     } else if (warp == NW_ACT + 1) {
       // ===================== weight producer (bulk copies) =====================
+      // ... and the residual / running-sum rows of the tile: the layer's `+ x` (models.py:72) and the sum over the three
+      // blocks (:239-245) are accumulated by the tensor core as D += R x I.  R = rows [t0, t0+256) of 32 channels,
+      // staged by TMA in the UMMA A layout; I = identity weight tile streamed through the weight ring like a tap.
       if (lane == 0) {
-        int stage = 0, phase = 0;
+        int stage = 0, phase = 0, rs = 0, rph = 0;
+        TileCursor cur{prefix};
         for (int w = blockIdx.x; w < total_tiles; w += gridDim.x) {
-          const int nt = w % n_tiles;
+          int b, t0, nt;
+          cur.locate(w, n_tiles, b, t0, nt);
           const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wt) + (size_t)nt * NCH * a.K * tile_bytes;
-          for (int c = 0; c < NCH; ++c)
+          for (int c = 0; c < NCH; ++c) {
             for (int s = 0; s < spc; ++s) {
               const int taps = min(tps, a.K - s * tps);
               const uint32_t bytes = (a.dbg & 2) ? 16u : (uint32_t)(taps * tile_bytes);
@@ -1152,6 +1164,29 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
               src += bytes;
               if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
             }
+            // residual chunk c of every stream rides behind conv chunk c (nchr <= NCH): the loads are spread over the
+            // tile, so the two-slot ring always has a chunk time to cover the TMA latency
+            if (RM && c < a.nchr)
+              for (int st = 0; st < nstreams_r; ++st) {
+                const CUtensorMap* rm = (st == 0 && a.rmma_r) ? &tmr : &tmq;
+                // identity tile of (column tile nt, input chunk nt * nchr + c)
+                const uint8_t* isrc = reinterpret_cast<const uint8_t*>(a.idw) + ((size_t)nt * NCH + nt * a.nchr + c) * tile_bytes;
+                mbar_wait_relaxed(BAR_WEMPTY(stage), phase ^ 1, 300);
+                mbar_expect_tx(BAR_WFULL(stage), (uint32_t)tile_bytes);
+                bulk_load(s_base + OFF_W + stage * W_STAGE_BYTES, isrc, (uint32_t)tile_bytes, BAR_WFULL(stage));
+                if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
+                mbar_wait_relaxed(BAR_REMPTY(rs), rph ^ 1, 300);
+                mbar_expect_tx(BAR_RFULL(rs), R_SLOT_BYTES);
+                const uint32_t dst = s_base + OFF_R + rs * R_SLOT_BYTES;
+                const int g0 = nt * (n_tile >> 3) + c * 4;
+#pragma unroll
+                for (int kg = 0; kg < 4; ++kg)
+#pragma unroll
+                  for (int h = 0; h < 2; ++h)
+                    tma_load_4d(dst + kg * (M_TILE * 16) + h * (128 * 16), rm, 0, t0 + h * 128, g0 + kg, b, BAR_RFULL(rs));
+                if (++rs == R_RING) { rs = 0; rph ^= 1; }
+              }
+          }
         }
       }
     } else if (warp == NW_ACT + 2) {
@@ -1173,7 +1208,8 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
         const uint32_t ringU = (ACT ? Z_BUF_BYTES : X_BUF_BYTES) >> 4;
         const uint32_t barF = ACT ? BAR_ZFULL(0) : BAR_XFULL(0), barE = ACT ? BAR_ZEMPTY(0) : BAR_XEMPTY(0);
         const bool lazy = ACT && a.Cin <= 96 && !(a.dbg & 4);
-        int stage = 0, phase = 0, rb = 0, rph = 0, it = 0;
+        const u64 hiR = make_sdesc(0, M_TILE * 16, 128);    // residual slot: 256 rows per 8-channel group
+        int stage = 0, phase = 0, rb = 0, rph = 0, it = 0, rr = 0, rrph = 0;
         for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++it) {
           const int as = (nacc == 2) ? (it & 1) : 0;
           mbar_wait(BAR_ACCEMPTY(as), ((((nacc == 2) ? (it >> 1) : it) & 1) ^ 1));   // epilogue has drained this stage
@@ -1182,7 +1218,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
           uint32_t accflag = 0;
           for (int c = 0; c < NCH; ++c) {
             // narrow layers are bound by the activation warps' issue slots: the issuer sleeps between polls there
-            if (lazy) mbar_wait_relaxed(barF + 8 * rb, rph, 64);
+            if (lazy) mbar_wait_relaxed(barF + 8 * rb, rph, 200);
             else mbar_wait(barF + 8 * rb, rph);
             tc_fence_after();
             const uint32_t aU = ring0 + (uint32_t)rb * ringU;
@@ -1207,6 +1243,24 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArgs
             }
             umma_commit(barE + 8 * rb);
             if (++rb == ND) { rb = 0; rph ^= 1; }
+            // + residual (+ running sum) chunk c: D += R x I, two K steps of 16 channels
+            if (RM && c < a.nchr)
+              for (int st = 0; st < nstreams_r; ++st) {
+                mbar_wait(BAR_RFULL(rr), rrph);
+                mbar_wait(BAR_WFULL(stage), phase);
+                tc_fence_after();
+                const uint32_t r0 = (s_base + OFF_R + rr * R_SLOT_BYTES) >> 4;
+                const uint32_t b0 = (s_base + OFF_W + stage * W_STAGE_BYTES) >> 4;
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                  umma_bf16(tm, hiR | (r0 + ks * (2 * M_TILE)), hiB | (b0 + ks * ksB), idesc, 1u);
+                  umma_bf16(tm + n_tile, hiR | (r0 + ks * (2 * M_TILE) + 128), hiB | (b0 + ks * ksB), idesc, 1u);
+                }
+                umma_commit(BAR_WEMPTY(stage));
+                if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
+                umma_commit(BAR_REMPTY(rr));
+                if (++rr == R_RING) { rr = 0; rrph ^= 1; }
+              }
           }
           umma_commit(BAR_ACCFULL(as));
         }

@@ -67,6 +67,22 @@ __global__ void k_pack_wt_tr(const float* __restrict__ wp, __nv_bfloat16* __rest
   }
 }
 
+// identity "weights" in the layout of a 1-tap conv, [ntile][chunk][1][4][n_tile][8]: the residual add as D += R x I
+__global__ void k_pack_identity(__nv_bfloat16* __restrict__ wt, int C, int n_tile, int NCH, int NT) {
+  const size_t total = (size_t)NT * NCH * 32 * n_tile;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int e = idx % 8;
+    size_t r = idx / 8;
+    const int n = r % n_tile; r /= n_tile;
+    const int kg = r % 4; r /= 4;
+    const int c = r % NCH;
+    const int nt = r / NCH;
+    const int co = nt * n_tile + n, ci = c * 32 + kg * 8 + e;
+    wt[idx] = __float2bfloat16_rn((co < C && ci < C && co == ci) ? 1.f : 0.f);
+  }
+}
+
 // a2 = 2*exp(alpha), nhb = -0.5/(exp(beta)+1e-9), zero-padded to a multiple of 32 channels
 __global__ void k_tc_params(const float* a, const float* invb, float* a2, float* nhb, int C, int Cpad) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -116,6 +132,7 @@ struct TcLayer {
   float* a2 = nullptr;
   float* nhb = nullptr;
   int n_tile = 0, n_tiles = 0, tps = 1, tmem_cols = 32, nch = 0;
+  __nv_bfloat16* idw = nullptr;   // identity tiles (square layers only): residual add on the tensor core
 };
 
 struct TcPlan {
@@ -171,6 +188,15 @@ static int build_layer(std::vector<void*>& owned, TcLayer& L, const ConvW& cw, c
   k_pack_wt<<<(int)std::min<size_t>((elems + 255) / 256, 8192), 256, 0, st>>>(cw.wp, L.wt, cw.Cin, cw.Cout, cw.K,
                                                                              L.n_tile, L.nch, L.n_tiles);
   BVG_CUDA(cudaGetLastError());
+  if (cw.Cin == cw.Cout && (L.n_tiles == 1 || L.n_tile % 32 == 0)) {
+    const size_t ie = (size_t)L.n_tiles * L.nch * 32 * L.n_tile;
+    if (!L.idw) {
+      BVG_CUDA(cudaMalloc((void**)&L.idw, ie * sizeof(__nv_bfloat16)));
+      owned.push_back(L.idw);
+    }
+    k_pack_identity<<<(int)std::min<size_t>((ie + 255) / 256, 4096), 256, 0, st>>>(L.idw, cw.Cout, L.n_tile, L.nch, L.n_tiles);
+    BVG_CUDA(cudaGetLastError());
+  }
   if (aw) {
     const int Cpad = L.nch * KC;
     if (!L.a2) {
@@ -316,11 +342,13 @@ struct TcLaunch {
   int out_tstride = 0;               // defaults to Tstride
   int st_lo = 0, st_hi = 0x7fffffff; // store range (rows) of a conv-mode launch
   __nv_bfloat16* zbuf = nullptr;     // scratch for the split form (act_blk.cuh), same geometry as x
+  int acc_rows = 0;                  // rows that exist behind acc_in / out (time-split windows); 0 = Tstride
 };
 
-template <int L, bool ACT>
-static int launch_inst(const CUtensorMap& map, const TcArgs& a, dim3 grid, cudaStream_t st) {
-  auto kern = k_amp_tc<L, ACT>;
+template <int L, bool ACT, bool RM>
+static int launch_inst_rm(const CUtensorMap& map, const CUtensorMap& mapr, const CUtensorMap& mapq, const TcArgs& a, dim3 grid,
+                          cudaStream_t st) {
+  auto kern = k_amp_tc<L, ACT, RM>;
   static bool attr = false;
   if (!attr) {
     BVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -336,9 +364,18 @@ static int launch_inst(const CUtensorMap& map, const TcArgs& a, dim3 grid, cudaS
     BVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, want));
     carve = want;
   }
-  kern<<<grid, NTHREADS, smem, st>>>(map, a);
+  kern<<<grid, NTHREADS, smem, st>>>(map, mapr, mapq, a);
   BVG_CUDA(cudaGetLastError());
   return 0;
+}
+
+// RM = the residual-add-by-identity-MMA code is compiled in (it costs the single-thread roles registers, and the narrow
+// many-tap layers that do not use it are bound by exactly those threads)
+template <int L, bool ACT>
+static int launch_inst(const CUtensorMap& map, const CUtensorMap& mapr, const CUtensorMap& mapq, const TcArgs& a, dim3 grid,
+                       cudaStream_t st) {
+  return (a.rmma_r || a.rmma_q) ? launch_inst_rm<L, ACT, true>(map, mapr, mapq, a, grid, st)
+                                : launch_inst_rm<L, ACT, false>(map, mapr, mapq, a, grid, st);
 }
 
 template <int NUB>
@@ -492,11 +529,39 @@ static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, cons
     a.xgroups = cw.Cin / 8;
     rc = (hc <= 16) ? launch_fir_inst<10>(*fm, a, grid, st) : launch_fir_inst<11>(*fm, a, grid, st);
   } else
+  {
+    // residual / running-sum add as identity MMAs (D += R x I) instead of loads + adds in the epilogue warps
+    static const bool rmma_on = [] { const char* e = getenv("BVG_RMMA"); return !e || atoi(e) != 0; }();
+    const CUtensorMap* mr = &map;
+    const CUtensorMap* mq = &map;
+    CUtensorMap tmpr, tmpq;
+    // Worth it unless the layer is bound by the MMA issue thread itself: narrow layers (small N, A-operand-fetch-bound
+    // MMAs of ~50 cycles whatever N) with many taps got slower with 4-8 more MMAs and two more hand-shakes per chunk
+    // (per-launch events, profiles/r01_rmma_ab.txt): threshold = 36 conv MMAs per tile.
+    const bool rmma_pays = cw.Cin >= 192 || L.nch * cw.K * 4 <= 36;
+    if (rmma_on && rmma_pays && !q.up && L.idw && (q.resid || q.acc_in)) {
+      TcPlan* t = p ? static_cast<TcPlan*>(p->tc) : nullptr;
+      rc = 0;
+      if (q.resid) {
+        mr = &tmpr;
+        rc = t ? get_map(t, q.resid, cw.Cout, a.Tstride, q.B, &mr, 0, 128) : make_map(q.resid, cw.Cout, a.Tstride, q.B, &tmpr, 0, 128);
+      }
+      if (!rc && q.acc_in) {
+        mq = &tmpq;
+        rc = t ? get_map(t, q.acc_in, cw.Cout, a.Tstride, q.B, &mq, q.acc_rows, 128)
+               : make_map(q.acc_in, cw.Cout, a.Tstride, q.B, &tmpq, q.acc_rows, 128);
+      }
+      if (rc) return rc;
+      a.idw = L.idw; a.nchr = (L.n_tile + 31) / 32;
+      a.rmma_r = q.resid ? 1 : 0; a.rmma_q = q.acc_in ? 1 : 0;
+      a.resid = nullptr; a.acc_in = nullptr;       // the epilogue warps see a plain conv
+    }
   // run length per activation thread: 4 warps x (8L - 6) valid rows must cover 256 + 2*hc z rows
-  if (!aw) rc = launch_inst<9, false>(map, a, grid, st);
-  else if (hc <= 4) rc = launch_inst<9, true>(map, a, grid, st);     // 4*(8*9-6)  = 264 >= 256 + 2*4
-  else if (hc <= 9) rc = launch_inst<10, true>(map, a, grid, st);    // 4*(8*10-6) = 296 >= 256 + 2*9 (2-way bank conflicts)
-  else rc = launch_inst<11, true>(map, a, grid, st);                 // 4*(8*11-6) = 328 >= 256 + 2*25
+  if (!aw) rc = launch_inst<9, false>(map, *mr, *mq, a, grid, st);
+  else if (hc <= 4) rc = launch_inst<9, true>(map, *mr, *mq, a, grid, st);     // 4*(8*9-6)  = 264 >= 256 + 2*4
+  else if (hc <= 9) rc = launch_inst<10, true>(map, *mr, *mq, a, grid, st);    // 4*(8*10-6) = 296 >= 256 + 2*9 (2-way bank conflicts)
+  else rc = launch_inst<11, true>(map, *mr, *mq, a, grid, st);                 // 4*(8*11-6) = 328 >= 256 + 2*25
+  }
   prof_end(p, st);
   if (p) ++p->last_launches;
   return rc;
@@ -515,6 +580,7 @@ struct StageIO {
   const int* d_len = nullptr;
   int st_lo_f = 0, st_hi_f = 0x7fffff;  // frames of the window whose output rows are stored in xs
   int cur_rows = 0;                     // rows of `cur` that exist behind the pointer (0 = Fs*rate[i])
+  int xs_rows = 0;                      // same for `xs`
   bool concurrent = true;
 };
 
@@ -639,6 +705,7 @@ static int tc_stage(bvg_plan* p, TcPlan* t, int i, const StageIO& io, cudaStream
         if (j > 0 && nstreams > 1) BVG_CUDA(cudaStreamWaitEvent(sq, t->ev_last[j - 1], 0));
         qb.out = io.xs;
         qb.acc_in = (j > 0) ? io.xs : nullptr;
+        qb.acc_rows = io.xs_rows;
         qb.div = (j == nk - 1) ? (float)nk : 1.f;
         qb.st_lo = io.st_lo_f * Ri;
         qb.st_hi = (io.st_hi_f >= 0x7fffff) ? 0x7fffffff : io.st_hi_f * Ri;
@@ -880,6 +947,7 @@ int tc_shard_run(bvg_plan* p, int phase, const void* latent, int latent_dtype, c
     // open so the zero rows past the end (conv padding for the next ConvTranspose1d) get written
     io.st_lo_f = hl; io.st_hi_f = hasr ? hl + own : 0x7fffff;
     io.cur_rows = (Fs - (H - hl)) * p->rate[i];
+    io.xs_rows = (Fs - (H - hl)) * p->rate[i + 1];
     io.concurrent = true;
     if ((rc = tc_stage(p, t, i, io, st))) return rc;
     // send my boundary rows of this stage's output to the neighbours (input halo of the next phase)
