@@ -126,6 +126,43 @@ __global__ void k_blk_to_cm(const __nv_bfloat16* __restrict__ x, float* __restri
   for (int e = 0; e < 8; ++e) out[((size_t)b * C + cg * 8 + e) * T + t] = __bfloat162float(v[e]);
 }
 
+// conv_post (C -> 1 channel, k taps, zero padding) + tanh (models.py:249-250) over z = activation_post(x), z blocked
+// bf16 [B][C/8][Tstride][8] as k_act_blk leaves it.  One thread per output sample; the k x C/8 16-byte rows it reads
+// are shared with its neighbours through L1.  Output in the caller's dtype (int16 = infer.py:892,911), zero past T_b.
+__global__ void __launch_bounds__(256) k_conv_post_blk(const __nv_bfloat16* __restrict__ z, const float* __restrict__ wp,
+                                                       const float* __restrict__ bias, void* __restrict__ out, int out_dtype,
+                                                       int groups, int K, int Tstride, const int* __restrict__ lengths,
+                                                       int rate) {
+  __shared__ float ws[8 * 16 * 16];                 // [C][K] tap weights, C <= 128, K <= 16
+  const int C = groups * 8;
+  for (int i = threadIdx.x; i < C * K; i += blockDim.x) ws[i] = wp[i];   // wp is [Cin][K][Cout = 1]
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= Tstride) return;
+  const int T = lengths ? lengths[b] * rate : Tstride;
+  float acc = 0.f;
+  if (t < T) {
+    acc = bias[0];
+    const int hk = (K - 1) / 2;
+    for (int j = 0; j < K; ++j) {
+      const int tt = t + j - hk;
+      if (tt < 0 || tt >= T) continue;
+      for (int g = 0; g < groups; ++g) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(z + (((size_t)b * groups + g) * Tstride + tt) * 8));
+        const uint32_t wds[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc = fmaf(ws[(g * 8 + 2 * e) * K + j], __uint_as_float(wds[e] << 16), acc);
+          acc = fmaf(ws[(g * 8 + 2 * e + 1) * K + j], __uint_as_float(wds[e] & 0xffff0000u), acc);
+        }
+      }
+    }
+    asm("tanh.approx.f32 %0, %1;" : "=f"(acc) : "f"(acc));
+  }
+  st_dyn(out, (size_t)b * Tstride + t, out_dtype, acc);
+}
+
 // ------------------------------------------------------------------------------ plan state
 struct TcLayer {
   __nv_bfloat16* wt = nullptr;
@@ -144,6 +181,8 @@ struct TcPlan {
   // the 3 AMP blocks of a stage are independent given xin (models.py:239-244): they run on three
   // streams (caller's + 2 owned) so their persistent grids back-fill each other's tails
   void* cbuf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  float* post_a2 = nullptr;                      // activation_post snake parameters in k_act_blk's form
+  float* post_nhb = nullptr;
   void* zbuf[3] = {nullptr, nullptr, nullptr};   // Activation1d output of the split layers (one per block stream)
   size_t zbuf_bytes = 0;
   size_t cbuf_bytes = 0;
@@ -236,6 +275,17 @@ int tc_plan_pack(bvg_plan* p, cudaStream_t st) {
   if ((rc = build_layer(t->owned, t->pre, p->conv_pre, nullptr, st))) return rc;
   for (int i = 0; i < p->n_stages; ++i)
     if ((rc = build_layer_tr(t->owned, t->ups[i], p->ups[i], p->cfg.upsample_rates[i], st))) return rc;
+  {
+    const int Cp = p->C[p->n_stages], Cpad = (Cp + KC - 1) / KC * KC;
+    if (!t->post_a2) {
+      BVG_CUDA(cudaMalloc((void**)&t->post_a2, Cpad * sizeof(float)));
+      BVG_CUDA(cudaMalloc((void**)&t->post_nhb, Cpad * sizeof(float)));
+      t->owned.push_back(t->post_a2);
+      t->owned.push_back(t->post_nhb);
+    }
+    k_tc_params<<<ceil_div(Cpad, 128), 128, 0, st>>>(p->act_post.a, p->act_post.invb, t->post_a2, t->post_nhb, Cp, Cpad);
+    BVG_CUDA(cudaGetLastError());
+  }
   for (int i = 0; i < p->n_stages; ++i)
     for (int j = 0; j < p->cfg.num_kernels; ++j) {
       const int n = i * p->cfg.num_kernels + j;
@@ -720,6 +770,35 @@ static int tc_stage(bvg_plan* p, TcPlan* t, int i, const StageIO& io, cudaStream
   return 0;
 }
 
+// activation_post + conv_post + tanh (models.py:248-250): the streaming Activation1d kernel, then a 24 -> 1 channel conv
+// + tanh that reads its bf16 rows.  (The SIMT kernel this replaces took 1.1 ms of a 25 ms step; it still serves the
+// shapes this one does not cover.)  `cur` may point into the middle of a stage buffer (time-split windows).
+static int tc_post(bvg_plan* p, TcPlan* t, const __nv_bfloat16* cur, void* wav_out, int wav_dtype, int B, int Tmax,
+                   const int* d_len, cudaStream_t st) {
+  int rc;
+  static const bool old_post = getenv("BVG_SIMT_POST") != nullptr;
+  const int S = p->n_stages, Cp = p->C[S], Kp = p->conv_post.K;
+  if (old_post || Cp % 8 != 0 || Cp > 128 || Kp > 16 || p->conv_post.Cout != 1)
+    return simt_post_blk(p, cur, wav_out, wav_dtype, B, Tmax, d_len, st);
+  const int Ts = Tmax * p->rate[S];
+  __nv_bfloat16* zpost = (__nv_bfloat16*)t->cbuf[0];        // the block buffers are idle after the last stage
+  TcLayer Lp;
+  Lp.a2 = t->post_a2; Lp.nhb = t->post_nhb;
+  ConvW cwp = p->conv_post;
+  TcLaunch qp;
+  qp.x = cur; qp.zbuf = zpost; qp.B = B; qp.Tstride = Ts; qp.rate = p->rate[S]; qp.d_len = d_len; qp.cls = 3;
+  qp.sm_count = p->sm_count;
+  if ((rc = launch_act_blk(p, cwp, &p->act_post, Lp, qp, st))) return rc;
+  dim3 gridp(ceil_div(Ts, 256), B);
+  prof_begin(p, st, 3, 2.0 * Cp * Kp * p->cur_sum_frames * p->rate[S], (2.0 * Cp + 4.0) * p->cur_sum_frames * p->rate[S]);
+  k_conv_post_blk<<<gridp, 256, 0, st>>>(zpost, p->conv_post.wp, p->conv_post.bias, wav_out, wav_dtype, Cp / 8, Kp, Ts, d_len,
+                                        p->rate[S]);
+  prof_end(p, st);
+  BVG_CUDA(cudaGetLastError());
+  ++p->last_launches;
+  return 0;
+}
+
 int tc_decode(bvg_plan* p, const void* latent, int latent_dtype, const int32_t* h_len, const int* d_len, int B,
               int Tmax, void* wav_out, int wav_dtype, cudaStream_t st) {
   TcPlan* t = static_cast<TcPlan*>(p->tc);
@@ -734,7 +813,7 @@ int tc_decode(bvg_plan* p, const void* latent, int latent_dtype, const int32_t* 
     io.B = B; io.Fs = Tmax; io.h_len = h_len; io.d_len = d_len;
     if ((rc = tc_stage(p, t, i, io, st))) return rc;
   }
-  return simt_post_blk(p, cur, wav_out, wav_dtype, B, Tmax, d_len, st);
+  return tc_post(p, t, cur, wav_out, wav_dtype, B, Tmax, d_len, st);
 }
 
 // ------------------------------------------------------------------------------ time split (P2P)
@@ -980,7 +1059,7 @@ int tc_shard_run(bvg_plan* p, int phase, const void* latent, int latent_dtype, c
   const int hl = hasl ? s->HF[S] : 0;
   const size_t esz = wav_dtype == BVG_F32 ? 4 : 2;
   void* tmp = p->ws[3];
-  if ((rc = simt_post_blk(p, buf[S & 1] + (size_t)(H - hl) * p->rate[S] * 8, tmp, wav_dtype, 1, Fs, s->d_win + 1 + S, st)))
+  if ((rc = tc_post(p, t, buf[S & 1] + (size_t)(H - hl) * p->rate[S] * 8, tmp, wav_dtype, 1, Fs, s->d_win + 1 + S, st)))
     return rc;
   BVG_CUDA(cudaMemcpyAsync(wav_out, (const char*)tmp + (size_t)hl * p->up_total * esz, (size_t)own * p->up_total * esz,
                            cudaMemcpyDeviceToDevice, st));
