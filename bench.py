@@ -414,7 +414,7 @@ def main():
             with open(tpath) as f:
                 tj = json.load(f)
             roofline["traffic"] = tj["amp_dram_bytes_per_launch"]
-            roofline["traffic_source"] = "profiles/r01_launches_v5_b16x10s_time_dram.csv (ncu, per launch avg)"
+            roofline["traffic_source"] = "profiles/r01_launches_s3_b16x10s_time_dram.csv (ncu, per launch avg)"
             roofline["algorithmic_bytes_per_launch"] = tj["amp_alg_bytes_per_launch"]
             roofline["algorithmic_flops_per_launch"] = tj["amp_flops_per_launch"]
         by_class = {}
