@@ -452,7 +452,7 @@ def main():
             "clocks": sampler.summary(),
             "wall_s_timed_region": wall_dev,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:     # the CPU arm is a single-GPU-run figure (rank 0 at N = 1 only)
             threads = os.cpu_count() or 1
             t = cpu_oracle_run(157, 2, threads)
             best = min(t)
