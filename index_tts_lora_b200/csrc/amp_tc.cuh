@@ -374,10 +374,21 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, float* bias_s, co
   const int cg_total = a.Cout >> 3;
         TileCursor cur{prefix};
     int it = 0;
+    // the utterance length of the NEXT tile is requested one tile early: a global load is an L2 round trip here
+    int Tin_next = a.Tmax;
+    auto ahead = [&](int w) {
+      if (w >= total_tiles || !a.lengths) return;
+      TileCursor c2 = cur;
+      int b, t0, nt;
+      c2.locate(w, n_tiles, b, t0, nt);
+      Tin_next = __ldg(a.lengths + b) * a.rate;
+    };
+    ahead(blockIdx.x);
     for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++it) {
       int b, t0, nt;
       cur.locate(w, n_tiles, b, t0, nt);
-      const int Tin = a.lengths ? a.lengths[b] * a.rate : a.Tmax;
+      const int Tin = Tin_next;
+      ahead(w + gridDim.x);
       const int T = Tin + extra;
       const int as = (nacc == 2) ? (it & 1) : 0;
       const int ause = (nacc == 2) ? (it >> 1) : it;
@@ -924,6 +935,108 @@ __device__ __forceinline__ void epilogue_pipe(const TcArgs& a, float* bias_s, ui
   }
 }
 
+// ------------------------------------------------------------------------------ ConvTranspose1d epilogue
+// Phase scatter of the (k/u)-tap implicit GEMM (models.py:157-163,232-236): accumulator column n = r*cphase + co holds
+// output time q*up + r - pad of channel co, q = the row's input time.  ncu on the generic epilogue_role showed these
+// launches idle on every pipe (issue 22 %, DRAM 16 %) behind ONE serial chain: ~2100 instructions per epilogue warp and
+// tile (an integer division per column group, 16-column steps).  Here: 32 columns per TMEM load, phase / channel-group
+// counters instead of divisions, packed adds, the next tile's utterance length requested a tile early.
+__device__ __forceinline__ void epilogue_up(const TcArgs& a, float* bias_s, const int* prefix, uint32_t bar_accfull0,
+                                            uint32_t bar_accempty0, uint32_t tmem, int nacc, int total_tiles, int extra,
+                                            int q, int lane, int etid) {
+  const int n_tile = a.n_tile, n_tiles = a.n_tiles;
+  const int gpp = a.cphase >> 3;                       // channel groups per phase
+  const int ncg = (a.up * a.cphase) >> 3;              // column groups in all
+  const int gstride = a.Tstride * 8;
+  TileCursor cur{prefix};
+  int it = 0;
+  int Tin_next = a.Tmax;
+  auto ahead = [&](int w) {
+    if (w >= total_tiles || !a.lengths) return;
+    TileCursor c2 = cur;
+    int b, t0, nt;
+    c2.locate(w, n_tiles, b, t0, nt);
+    Tin_next = __ldg(a.lengths + b) * a.rate;
+  };
+  ahead(blockIdx.x);
+  for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++it) {
+    int b, t0, nt;
+    cur.locate(w, n_tiles, b, t0, nt);
+    const int Tin = Tin_next;
+    ahead(w + gridDim.x);
+    const int T = Tin + extra, Tout = Tin * a.up;
+    const int as = (nacc == 2) ? (it & 1) : 0;
+    const int ause = (nacc == 2) ? (it >> 1) : it;
+    float* bs = bias_s + as * 256;
+    if (a.bias_b || n_tiles > 1 || it < nacc) {                       // bias row changes with (b, nt) only
+      asm volatile("bar.sync 1, 128;" ::: "memory");                  // previous user of bias_s[as] is done
+      for (int i = etid; i < n_tile; i += 128) {
+        int co = nt * n_tile + i;
+        float v = 0.f;
+        if (co < a.up * a.cphase) {
+          co %= a.cphase;
+          v = __ldg(a.bias + co);
+          if (a.bias_b) v += __ldg(a.bias_b + (size_t)b * a.bias_b_stride + co);
+        }
+        bs[i] = v;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    __nv_bfloat16* outp = a.out + (size_t)b * gpp * a.Tstride * 8;   // this utterance's block
+    const int cgn0 = nt * (n_tile >> 3);
+    const int ng = min(n_tile >> 3, ncg - cgn0);                      // live column groups of this tile
+    const int r0 = cgn0 / gpp, cg0 = cgn0 - r0 * gpp;                 // phase / channel group of the first one
+    if (q == 0) mbar_wait_relaxed(bar_accfull0 + 8 * as, ause & 1, 100);
+    asm volatile("bar.sync 2, 128;" ::: "memory");
+    tc_fence_after();
+    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * n_tile);
+#pragma unroll 1
+    for (int mb = 0; mb < 2; ++mb) {
+      const int tq = t0 + mb * 128 + q * 32 + lane;                   // input time of this thread's row
+      const int tb = tq * a.up - a.pad;                               // output time of phase 0
+      int r = r0, cg = cg0;
+#pragma unroll 1
+      for (int g0 = 0; g0 < ng; g0 += 4) {                            // 4 column groups = 32 accumulator columns
+        uint32_t v[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+            "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr + (uint32_t)(mb * n_tile + g0 * 8)));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          if (g0 + kk < ng) {
+            const int to = tb + r;
+            if (tq < T && to >= 0 && to < Tout) {
+              const ulonglong2 b01 = *reinterpret_cast<const ulonglong2*>(bs + (g0 + kk) * 8);
+              const ulonglong2 b23 = *reinterpret_cast<const ulonglong2*>(bs + (g0 + kk) * 8 + 4);
+              const u64 f0 = add2(pk(__uint_as_float(v[kk * 8 + 0]), __uint_as_float(v[kk * 8 + 1])), b01.x);
+              const u64 f1 = add2(pk(__uint_as_float(v[kk * 8 + 2]), __uint_as_float(v[kk * 8 + 3])), b01.y);
+              const u64 f2 = add2(pk(__uint_as_float(v[kk * 8 + 4]), __uint_as_float(v[kk * 8 + 5])), b23.x);
+              const u64 f3 = add2(pk(__uint_as_float(v[kk * 8 + 6]), __uint_as_float(v[kk * 8 + 7])), b23.y);
+              float l0, h0, l1, h1, l2, h2, l3, h3;
+              upk(f0, l0, h0); upk(f1, l1, h1); upk(f2, l2, h2); upk(f3, l3, h3);
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(l0, h0), p1 = __floats2bfloat162_rn(l1, h1);
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(l2, h2), p3 = __floats2bfloat162_rn(l3, h3);
+              *reinterpret_cast<uint4*>(outp + cg * gstride + to * 8) =
+                  make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                             *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+            }
+            if (++cg == gpp) { cg = 0; ++r; }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_accempty0 + 8 * as);
+  }
+}
+
 // ------------------------------------------------------------------------------ the kernel
 // Persistent: grid = min(#tiles, #SMs); every role walks the same static tile sequence
 // w = blockIdx.x, +gridDim.x, ... (tile = 256 rows x n_tile columns of one utterance; column
@@ -936,7 +1049,10 @@ template <int REGS>
 __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
 
 
-template <int L, bool ACT, bool RM>
+// EPI selects the one epilogue compiled into an instantiation (0 = conv, one column tile; 1 = conv, several column
+// tiles; 2 = ConvTranspose1d phase scatter): with all of them behind run-time branches in one function, adding a path
+// changed the register allocation of the others (measured: +30 us on the C = 24 residual layers).
+template <int L, bool ACT, bool RM, int EPI>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmr,
          const __grid_constant__ CUtensorMap tmq, const __grid_constant__ TcArgs a) {
@@ -1269,21 +1385,15 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
   } else {
     // ===================== epilogue warps: TMEM -> (+bias, +resid, +sum, /div) -> bf16 -> HBM ====
     reg_dec<64>();
-    if (a.up == 0 && n_tiles == 1 && !(a.dbg & 1024))   // conv mode: the pipelined packed-math epilogue
+    if constexpr (EPI == 0)
       epilogue_pipe<false>(a, bias_s, smem + off_r(NX, NZ, W_STAGES), prefix, BAR_ACCFULL(0), BAR_ACCEMPTY(0), tmem, nacc, total_tiles, warp & 3, lane,
                            threadIdx.x - (NW_ACT + 4) * 32);
-    else if (a.up == 0 && !(a.dbg & 1024))
+    else if constexpr (EPI == 1)
       epilogue_pipe<true>(a, bias_s, smem + off_r(NX, NZ, W_STAGES), prefix, BAR_ACCFULL(0), BAR_ACCEMPTY(0), tmem, nacc, total_tiles, warp & 3, lane,
                           threadIdx.x - (NW_ACT + 4) * 32);
-    else if (a.up == 0 && n_tiles == 1)
-      epilogue_fir<16, false>(a, bias_s, prefix, BAR_ACCFULL(0), BAR_ACCEMPTY(0), tmem, nacc, total_tiles, warp & 3, lane,
-                              threadIdx.x - (NW_ACT + 4) * 32);
-    else if (a.up == 0)
-      epilogue_fir<16, true>(a, bias_s, prefix, BAR_ACCFULL(0), BAR_ACCEMPTY(0), tmem, nacc, total_tiles, warp & 3, lane,
-                             threadIdx.x - (NW_ACT + 4) * 32);
     else
-      epilogue_role(a, bias_s, prefix, BAR_ACCFULL(0), BAR_ACCEMPTY(0), tmem, nacc, total_tiles, extra, warp & 3, lane,
-                    threadIdx.x - (NW_ACT + 4) * 32);
+      epilogue_up(a, bias_s, prefix, BAR_ACCFULL(0), BAR_ACCEMPTY(0), tmem, nacc, total_tiles, extra, warp & 3, lane,
+                  threadIdx.x - (NW_ACT + 4) * 32);
   }
   tc_fence_before();
   __syncthreads();

@@ -395,10 +395,10 @@ struct TcLaunch {
   int acc_rows = 0;                  // rows that exist behind acc_in / out (time-split windows); 0 = Tstride
 };
 
-template <int L, bool ACT, bool RM>
+template <int L, bool ACT, bool RM, int EPI>
 static int launch_inst_rm(const CUtensorMap& map, const CUtensorMap& mapr, const CUtensorMap& mapq, const TcArgs& a, dim3 grid,
                           cudaStream_t st) {
-  auto kern = k_amp_tc<L, ACT, RM>;
+  auto kern = k_amp_tc<L, ACT, RM, EPI>;
   static bool attr = false;
   if (!attr) {
     BVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -424,8 +424,14 @@ static int launch_inst_rm(const CUtensorMap& map, const CUtensorMap& mapr, const
 template <int L, bool ACT>
 static int launch_inst(const CUtensorMap& map, const CUtensorMap& mapr, const CUtensorMap& mapq, const TcArgs& a, dim3 grid,
                        cudaStream_t st) {
-  return (a.rmma_r || a.rmma_q) ? launch_inst_rm<L, ACT, true>(map, mapr, mapq, a, grid, st)
-                                : launch_inst_rm<L, ACT, false>(map, mapr, mapq, a, grid, st);
+  if (a.up) {
+    if constexpr (!ACT) return launch_inst_rm<L, false, false, 2>(map, mapr, mapq, a, grid, st);
+    else return fail(BVG_ERR_STATE, "ConvTranspose1d launches are never activated");
+  }
+  const bool rm = a.rmma_r || a.rmma_q;
+  if (a.n_tiles == 1)
+    return rm ? launch_inst_rm<L, ACT, true, 0>(map, mapr, mapq, a, grid, st) : launch_inst_rm<L, ACT, false, 0>(map, mapr, mapq, a, grid, st);
+  return rm ? launch_inst_rm<L, ACT, true, 1>(map, mapr, mapq, a, grid, st) : launch_inst_rm<L, ACT, false, 1>(map, mapr, mapq, a, grid, st);
 }
 
 template <int NUB>
