@@ -922,10 +922,14 @@ __device__ __forceinline__ void epilogue_pipe_t(const TcArgs& a, float* bias_s, 
   }
 }
 
-template <bool MULTI>
+template <bool MULTI, bool PLAIN_ONLY>
 __device__ __forceinline__ void epilogue_pipe(const TcArgs& a, float* bias_s, uint8_t* rstage, const int* prefix,
                                               uint32_t bar_accfull0, uint32_t bar_accempty0, uint32_t tmem, int nacc,
                                               int total_tiles, int q, int lane, int etid) {
+  if constexpr (PLAIN_ONLY) {
+    epilogue_pipe_t<4, false, false, MULTI>(a, bias_s, rstage, prefix, bar_accfull0, bar_accempty0, tmem, nacc, total_tiles, q, lane, etid);
+    return;
+  }
   if (a.resid) {
     if (a.acc_in) epilogue_pipe_t<2, true, true, MULTI>(a, bias_s, rstage, prefix, bar_accfull0, bar_accempty0, tmem, nacc, total_tiles, q, lane, etid);
     else epilogue_pipe_t<4, true, false, MULTI>(a, bias_s, rstage, prefix, bar_accfull0, bar_accempty0, tmem, nacc, total_tiles, q, lane, etid);
@@ -1385,11 +1389,12 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
   } else {
     // ===================== epilogue warps: TMEM -> (+bias, +resid, +sum, /div) -> bf16 -> HBM ====
     reg_dec<64>();
+    // (instantiations whose residual goes through the tensor core, RM, only ever see a plain conv here)
     if constexpr (EPI == 0)
-      epilogue_pipe<false>(a, bias_s, smem + off_r(NX, NZ, W_STAGES), prefix, BAR_ACCFULL(0), BAR_ACCEMPTY(0), tmem, nacc, total_tiles, warp & 3, lane,
+      epilogue_pipe<false, RM>(a, bias_s, smem + off_r(NX, NZ, W_STAGES), prefix, BAR_ACCFULL(0), BAR_ACCEMPTY(0), tmem, nacc, total_tiles, warp & 3, lane,
                            threadIdx.x - (NW_ACT + 4) * 32);
     else if constexpr (EPI == 1)
-      epilogue_pipe<true>(a, bias_s, smem + off_r(NX, NZ, W_STAGES), prefix, BAR_ACCFULL(0), BAR_ACCEMPTY(0), tmem, nacc, total_tiles, warp & 3, lane,
+      epilogue_pipe<true, RM>(a, bias_s, smem + off_r(NX, NZ, W_STAGES), prefix, BAR_ACCFULL(0), BAR_ACCEMPTY(0), tmem, nacc, total_tiles, warp & 3, lane,
                           threadIdx.x - (NW_ACT + 4) * 32);
     else
       epilogue_up(a, bias_s, prefix, BAR_ACCFULL(0), BAR_ACCEMPTY(0), tmem, nacc, total_tiles, extra, warp & 3, lane,

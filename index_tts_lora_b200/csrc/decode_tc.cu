@@ -531,7 +531,8 @@ static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, cons
   // MMAs of the next tile during the epilogue; 4 z buffers let the activation warps run ahead meanwhile.
   // ring depths (22 / 21.5 / 16 KB per slot; 32 KB go to the epilogue's residual staging).  Narrow layers stream x
   // tile after tile (one chunk per tile) and need little weight staging; wide layers walk 6-24 chunks per tile.
-  if (cw.Cin <= 96 && !q.up) { a.nx = 3; a.nz = 3; a.wst = 3; }
+  if (!aw) { a.nx = 3; a.nz = 2; a.wst = 4; }                       // plain conv / ConvTranspose1d: the MMA reads the x ring
+  else if (cw.Cin <= 96) { a.nx = 3; a.nz = 3; a.wst = 3; }
   else { a.nx = 2; a.nz = 3; a.wst = 4; }
   {
     static int ov[3] = {-1, -1, -1};      // BVG_RINGS="nx,nz,wst": experiment hook
