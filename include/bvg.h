@@ -203,6 +203,13 @@ int bvg_set_tc_fir_max_channels(int max_c);
  * built-in threshold.  Returns the previous value. */
 int bvg_set_tc_split_min_channels(int min_c);
 
+/* bf16 path: the `+ x` of a conv pair (models.py:72) and the running sum over the AMP blocks (:239-245) are accumulated
+ * by the tensor core as D += R x I (TMA-staged rows, identity weight tile) on the layers where that is faster than
+ * loading and adding the rows in the epilogue warps (every C >= 192 layer; narrow layers with <= 36 conv MMAs per
+ * tile).  on = 0 keeps every add in the epilogue.  Both forms add the same bf16 rows to the same fp32 accumulator; only
+ * the order of the additions differs.  Process-wide; default on (or BVG_RMMA=0 at first use).  Returns the previous value. */
+int bvg_set_tc_residual_mma(int on);
+
 /* ---- per-op entry points (tests, and the reference's own native-op boundary) ---------- */
 
 /* Supersedes anti_alias_activation_cuda.forward(input, up_filter, down_filter, alpha, beta)

@@ -81,6 +81,7 @@ SYMBOLS = {
     "bvg_plan_read_profile": (_I, [_P, C.POINTER(BvgProfile)]),
     "bvg_set_tc_fir_max_channels": (_I, [_I]),
     "bvg_set_tc_split_min_channels": (_I, [_I]),
+    "bvg_set_tc_residual_mma": (_I, [_I]),
     "bvg_activation1d": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P]),
     "bvg_amp_layer": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P]),
     "bvg_conv_transpose1d": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _P]),

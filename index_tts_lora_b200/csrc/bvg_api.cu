@@ -678,6 +678,7 @@ int bvg_plan_set_profiling(bvg_plan* p, int enable) {
 
 int bvg_set_tc_fir_max_channels(int max_c) { return bvg::tc_set_fir_max_c(max_c); }
 int bvg_set_tc_split_min_channels(int min_c) { return bvg::tc_set_split_min_c(min_c); }
+int bvg_set_tc_residual_mma(int on) { return bvg::tc_set_residual_mma(on); }
 
 int bvg_plan_read_profile(bvg_plan* p, bvg_profile* out) {
   BVG_REQUIRE(p && out, "bvg_plan_read_profile: null argument");

@@ -479,6 +479,21 @@ static int split_min_c() {
 }
 static bool split_layer(int Cin) { return split_min_c() > 0 && Cin >= split_min_c(); }
 
+// Residual / running-sum add by identity MMAs (amp_tc.cuh) on the layers where it pays; off = always in the epilogue.
+static int g_rmma = -1;
+int tc_set_residual_mma(int on) {
+  const int old = g_rmma < 0 ? 1 : g_rmma;
+  g_rmma = on ? 1 : 0;
+  return old;
+}
+static bool residual_mma_on() {
+  if (g_rmma < 0) {
+    const char* e = getenv("BVG_RMMA");
+    g_rmma = (!e || atoi(e) != 0) ? 1 : 0;
+  }
+  return g_rmma != 0;
+}
+
 static int launch_act_blk(bvg_plan* p, const ConvW& cw, const ActW* aw, const TcLayer& L, const TcLaunch& q,
                           cudaStream_t st) {
   AbArgs b{};
@@ -588,7 +603,7 @@ static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, cons
   } else
   {
     // residual / running-sum add as identity MMAs (D += R x I) instead of loads + adds in the epilogue warps
-    static const bool rmma_on = [] { const char* e = getenv("BVG_RMMA"); return !e || atoi(e) != 0; }();
+    const bool rmma_on = residual_mma_on();
     const CUtensorMap* mr = &map;
     const CUtensorMap* mq = &map;
     CUtensorMap tmpr, tmpq;

@@ -14,6 +14,7 @@ int tc_amp_layer(const float* x, float* y, const float* resid, int B, int C_in, 
                  const float* beta, int logscale, cudaStream_t st);
 int tc_set_fir_max_c(int v);
 int tc_set_split_min_c(int v);
+int tc_set_residual_mma(int on);
 // time-split P2P decode (decode_tc.cu)
 int tc_shard_setup(bvg_plan* p, const bvg_shard_geom* g, cudaStream_t st);
 int tc_shard_halo_frames(bvg_plan* p);

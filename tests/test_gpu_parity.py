@@ -498,3 +498,53 @@ def test_full_generator_bf16_split_snr():
     snr = _snr(ref, wav)
     print("bf16 split form SNR dB", snr)
     assert snr > BF16_SNR_DB, snr
+
+
+# ============================================================================= residual add on the tensor core
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,d", [(3, 1), (11, 5)])
+@pytest.mark.parametrize("C,T", [(24, 700), (48, 1500), (96, 5), (192, 300), (384, 257), (768, 70)])
+def test_amp_layer_bf16_residual_mma_vs_epilogue_add(k, d, C, T):
+    """The layer's `+ x` accumulated by the tensor core (D += R x I, amp_tc.cuh) against the same add in the epilogue
+    warps: same bf16 rows, same fp32 accumulator, different order of additions -> equal to bf16 rounding, and both
+    within the per-layer bar against the fp32 oracle.  C = 48 / 96 with k = 11 exercise the layers that keep the
+    epilogue add; T = 5 the sequence edges; 384 / 768 several column tiles."""
+    from index_tts_lora_b200.models import AMPBlock1
+    from index_tts_lora_b200.ops import amp_layer
+    from index_tts_lora_b200 import synth, _lib
+    from index_tts_lora_b200.config import AttrDict
+    O = _oracle()
+    dev = _dev()
+    lib = _lib.load()
+    blk = AMPBlock1(AttrDict(snake_logscale=True), C, k, (d, d, d), activation="snakebeta")
+    sd = synth.synth_state_dict(blk.state_dict(), seed=k * 100 + d, profile="stress")
+    blk.load_state_dict(sd)
+    x = torch.randn(2, C, T, generator=synth._gen(1, f"x{C}{T}"))
+    r = torch.randn(2, C, T, generator=synth._gen(2, f"r{C}{T}"))
+    ref = O.amp_layer(x, sd, "activations.0", "convs1.0", k, d) + r
+    old = lib.bvg_set_tc_residual_mma(1)
+    try:
+        y_mma = amp_layer(x.to(dev), blk.convs1[0], blk.activations[0], resid=r.to(dev), precision="bf16").cpu()
+        lib.bvg_set_tc_residual_mma(0)
+        y_epi = amp_layer(x.to(dev), blk.convs1[0], blk.activations[0], resid=r.to(dev), precision="bf16").cpu()
+    finally:
+        lib.bvg_set_tc_residual_mma(old)
+    assert _snr(ref, y_mma) > 35.0, _snr(ref, y_mma)
+    assert _snr(ref, y_epi) > 35.0, _snr(ref, y_epi)
+    assert _snr(y_epi, y_mma) > 45.0, _snr(y_epi, y_mma)
+
+
+@pytest.mark.gpu
+def test_full_generator_bf16_epilogue_add_snr():
+    """BASELINE config 2 with every residual add kept in the epilogue warps (the form before D += R x I): same bar."""
+    from index_tts_lora_b200.config import default_config
+    from index_tts_lora_b200 import _lib
+    lib = _lib.load()
+    old = lib.bvg_set_tc_residual_mma(0)
+    try:
+        wav, ref, *_ = _run_case("full_f157_init", default_config(), "bf16")
+    finally:
+        lib.bvg_set_tc_residual_mma(old)
+    snr = _snr(ref, wav)
+    print("bf16, epilogue residual add: SNR dB", snr)
+    assert snr > BF16_SNR_DB, snr
