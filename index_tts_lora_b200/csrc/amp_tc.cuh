@@ -12,15 +12,18 @@
 // across the 32 lanes of a warp (512 B runs).
 //
 // CTA tile: 256 time rows (two M=128 accumulators) x n_tile output channels (<= 256), looping
-// over C_in in chunks of 32 channels:
-//   warp 8      TMA producer: x rows [t0-32, t0+288) of the chunk -> xbuf[2]   (8 boxes of {8,160})
-//   warp 9      weight producer: per-(chunk,tap) bf16 tiles [4][n_tile][8] via cp.async.bulk -> ring[4]
-//   warps 0-7   activation: x -> 2x kaiser-sinc FIR up -> SnakeBeta -> FIR down -> bf16 z tile in the
+// over C_in in chunks of 32 channels.  Persistent grid (one CTA per SM), 24 warps:
+//   warps 0-15  activation: x -> 2x kaiser-sinc FIR up -> SnakeBeta -> FIR down -> bf16 z tile in the
 //               UMMA A layout (fp32 math on packed f32x2 registers, two channels per thread, one
-//               run of L consecutive rows per thread); afterwards the same warps run the epilogue
-//   warp 10     MMA issuer: for every tap j, M block, K step: tcgen05.mma.kind::f16
-//               A = z tile rows (mb*128 + j*dil ..), B = weight tile, D = TMEM[mb*n_tile ..]
-// Synchronisation is mbarrier-only inside the main loop.
+//               run of L consecutive rows per thread, neighbours' samples by warp shuffle)
+//   warp 16     TMA producer: x rows [t0-32, t0+288) of the chunk -> x ring   (8 boxes of {8,160})
+//   warp 17     weight producer: per-(chunk,tap) bf16 tiles [4][n_tile][8] via cp.async.bulk -> weight ring;
+//               also the residual / running-sum rows (TMA) and identity tiles of D += R x I (RM)
+//   warp 18     MMA issuer: for every tap j, M block, K step: tcgen05.mma.kind::f16
+//               A = z tile rows (mb*128 + j*dil ..), B = weight tile, D = TMEM[stage][mb*n_tile ..]
+//   warps 20-23 epilogue: TMEM -> +bias (+cond) [+resid] [+sum] [/3] -> bf16 -> HBM; one of three variants
+//               per instantiation (EPI): conv / conv with several column tiles / ConvTranspose1d scatter
+// Synchronisation is mbarrier-only inside the main loop; DESIGN.md §4.1 has the measurements behind each choice.
 #pragma once
 #include <cuda.h>
 
@@ -1166,7 +1169,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
             if ((smask >> r) & 1u) zk[(rowS + r) * 4] = 0u;
         }
       }
-      // Shared memory takes all but ~4 KB of the SM's L1, so every global load below is an L2 round trip (0.3-1 us
+      // Shared memory leaves the SM little L1, so every global load below is an L2 round trip (0.3-1 us
       // under load).  The utterance length of the NEXT tile and the snake parameters of the NEXT chunk are therefore
       // requested one iteration early (ncu: 40 % of the activation warps' stall samples sat on the length load).
       TileCursor cur{prefix};
@@ -1313,7 +1316,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
       // ===================== MMA issuer =====================
       // One thread, 32 registers: everything loop-carried is kept to a minimum (one operand ring index instead of
       // separate x / z cursors, descriptors rebuilt from 32-bit address units) because a spilled value costs an L2
-      // round trip here — shared memory leaves the SM ~4 KB of L1 — and this thread is the serial link between the
+      // round trip here — shared memory leaves the SM little L1 — and this thread is the serial link between the
       // activation warps and the epilogue.
       if (lane == 0) {
         const uint32_t idesc = make_idesc_bf16(128, n_tile);
