@@ -548,3 +548,38 @@ def test_full_generator_bf16_epilogue_add_snr():
     snr = _snr(ref, wav)
     print("bf16, epilogue residual add: SNR dB", snr)
     assert snr > BF16_SNR_DB, snr
+
+
+@pytest.mark.gpu
+def test_ragged_batch_bf16_residual_mma_vs_epilogue_add():
+    """Mixed-length batch at the real config: rows past an utterance's end inside its last tile reach the tensor-core
+    residual add as whatever the buffers hold (they are never stored); the valid rows must agree with the epilogue
+    form to bf16 rounding and the tails must stay zero."""
+    from index_tts_lora_b200.config import default_config
+    from index_tts_lora_b200 import synth, _lib
+    from index_tts_lora_b200.models import BigVGAN
+    dev = _dev()
+    lib = _lib.load()
+    h = default_config()
+    m = BigVGAN(h)
+    m.load_state_dict(synth.synth_state_dict(m.state_dict(), seed=1234, profile="init"))
+    m = m.to(dev).eval()
+    m.precision = "bf16"
+    lengths = [23, 7, 1, 40]
+    lat = synth.synth_latent(len(lengths), max(lengths), h.gpt_dim, seed=3).to(dev)
+    emb = m.speaker_embedding(synth.synth_mel(1, 120, h.num_mels, seed=4).to(dev)).expand(len(lengths), -1, -1)
+    # poison the workspace first: a longer decode leaves non-zero rows behind every shorter utterance
+    m.decode(synth.synth_latent(len(lengths), 48, h.gpt_dim, seed=9).to(dev), emb, out_dtype=torch.float32)
+    old = lib.bvg_set_tc_residual_mma(1)
+    try:
+        y_mma = m.decode(lat, emb, lengths=lengths, out_dtype=torch.float32).cpu()
+        lib.bvg_set_tc_residual_mma(0)
+        y_epi = m.decode(lat, emb, lengths=lengths, out_dtype=torch.float32).cpu()
+    finally:
+        lib.bvg_set_tc_residual_mma(old)
+    assert torch.isfinite(y_mma).all()
+    for b, L in enumerate(lengths):
+        snr = _snr(y_epi[b, :, : L * 1024], y_mma[b, :, : L * 1024])
+        assert snr > 40.0, (b, L, snr)
+        if L < max(lengths):
+            assert y_mma[b, :, L * 1024:].abs().max().item() == 0.0
