@@ -631,7 +631,7 @@ static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, cons
   // run length per activation thread: 4 warps x (8L - 6) valid rows must cover 256 + 2*hc z rows
   if (!aw) rc = launch_inst<9, false>(map, *mr, *mq, a, grid, st);
   else if (hc <= 4) rc = launch_inst<9, true>(map, *mr, *mq, a, grid, st);     // 4*(8*9-6)  = 264 >= 256 + 2*4
-  else if (hc <= 9) rc = launch_inst<10, true>(map, *mr, *mq, a, grid, st);    // 4*(8*10-6) = 296 >= 256 + 2*9 (2-way bank conflicts)
+  else if (hc <= 20) rc = launch_inst<10, true>(map, *mr, *mq, a, grid, st);   // 4*(8*10-6) = 296 >= 256 + 2*20 (2-way bank conflicts)
   else rc = launch_inst<11, true>(map, *mr, *mq, a, grid, st);                 // 4*(8*11-6) = 328 >= 256 + 2*25
   }
   prof_end(p, st);
