@@ -169,6 +169,26 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, u64 adesc, u64 bdesc,
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+// Warp-convergent forms: every lane executes the statement with identical (uniform) operands and the instruction
+// itself is predicated on the elected lane.  Issued from a divergent `if (lane == 0)` region, ptxas wraps every
+// UTCHMMA in an ELECT / BRA.U.ANY waterfall plus R2UR moves (~15 instructions and ~50 cycles per MMA).
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void umma_bf16_e(uint32_t leader, uint32_t tmem_d, u64 adesc, u64 bdesc, uint32_t idesc,
+                                            uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 e, %5, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void umma_commit_e(uint32_t leader, uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\tsetp.ne.b32 e, %1, 0;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(bar), "r"(leader) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -1318,7 +1338,8 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
       // separate x / z cursors, descriptors rebuilt from 32-bit address units) because a spilled value costs an L2
       // round trip here — shared memory leaves the SM little L1 — and this thread is the serial link between the
       // activation warps and the epilogue.
-      if (lane == 0) {
+      {
+        const uint32_t leader = elect_one();      // the whole warp walks the loop; one lane issues
         const uint32_t idesc = make_idesc_bf16(128, n_tile);
         const uint32_t lboA = (ACT ? ZR : XRA) * 16;
         const uint32_t lboB = (uint32_t)n_tile * 16;
@@ -1353,18 +1374,18 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
               for (int tj = 0; tj < taps; ++tj) {
                 const uint32_t a0 = aU + (uint32_t)((s * tps + tj) * a.dil);
                 const uint32_t b0 = wU + (uint32_t)tj * tileU;
-                umma_bf16(tm, hiA | a0, hiB | b0, idesc, accflag);
+                umma_bf16_e(leader, tm, hiA | a0, hiB | b0, idesc, accflag);
                 if (!(a.dbg & 1)) {
-                  umma_bf16(tm, hiA | (a0 + ksA), hiB | (b0 + ksB), idesc, 1u);
-                  umma_bf16(tm + n_tile, hiA | (a0 + 128), hiB | b0, idesc, accflag);
-                  umma_bf16(tm + n_tile, hiA | (a0 + 128 + ksA), hiB | (b0 + ksB), idesc, 1u);
+                  umma_bf16_e(leader, tm, hiA | (a0 + ksA), hiB | (b0 + ksB), idesc, 1u);
+                  umma_bf16_e(leader, tm + n_tile, hiA | (a0 + 128), hiB | b0, idesc, accflag);
+                  umma_bf16_e(leader, tm + n_tile, hiA | (a0 + 128 + ksA), hiB | (b0 + ksB), idesc, 1u);
                 }
                 accflag = 1u;
               }
-              umma_commit(BAR_WEMPTY(stage));          // weight stage free once these MMAs retire
+              umma_commit_e(leader, BAR_WEMPTY(stage));          // weight stage free once these MMAs retire
               if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
             }
-            umma_commit(barE + 8 * rb);
+            umma_commit_e(leader, barE + 8 * rb);
             if (++rb == ND) { rb = 0; rph ^= 1; }
             // + residual (+ running sum) chunk c: D += R x I, two K steps of 16 channels
             if (RM && c < a.nchr)
@@ -1376,16 +1397,16 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
                 const uint32_t b0 = (s_base + OFF_W + stage * W_STAGE_BYTES) >> 4;
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks) {
-                  umma_bf16(tm, hiR | (r0 + ks * (2 * M_TILE)), hiB | (b0 + ks * ksB), idesc, 1u);
-                  umma_bf16(tm + n_tile, hiR | (r0 + ks * (2 * M_TILE) + 128), hiB | (b0 + ks * ksB), idesc, 1u);
+                  umma_bf16_e(leader, tm, hiR | (r0 + ks * (2 * M_TILE)), hiB | (b0 + ks * ksB), idesc, 1u);
+                  umma_bf16_e(leader, tm + n_tile, hiR | (r0 + ks * (2 * M_TILE) + 128), hiB | (b0 + ks * ksB), idesc, 1u);
                 }
-                umma_commit(BAR_WEMPTY(stage));
+                umma_commit_e(leader, BAR_WEMPTY(stage));
                 if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
-                umma_commit(BAR_REMPTY(rr));
+                umma_commit_e(leader, BAR_REMPTY(rr));
                 if (++rr == R_RING) { rr = 0; rrph ^= 1; }
               }
           }
-          umma_commit(BAR_ACCFULL(as));
+          umma_commit_e(leader, BAR_ACCFULL(as));
         }
       }
     }
