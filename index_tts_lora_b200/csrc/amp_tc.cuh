@@ -372,8 +372,9 @@ __device__ __noinline__ void act_run_edge(const uint32_t* xk, uint32_t* zk, int 
 }
 
 // ------------------------------------------------------------------------------ epilogue role
-// Four warps (q = TMEM lane quarter, etid = 0..127): TMEM -> (+bias, +cond, +resid, +sum, /div) -> bf16 -> HBM.
-// Shared by k_amp_tc and k_amp_fir (amp_fir.cuh); walks the same static tile sequence as the other roles.
+// Four warps (q = TMEM lane quarter, etid = 0..127): TMEM -> (+bias, +cond, +resid, +sum, /div) -> bf16 -> HBM; they walk
+// the same static tile sequence as the other roles.  (The generic first-generation epilogue that also did the
+// ConvTranspose1d scatter was retired in favour of epilogue_pipe / epilogue_up below; epilogue_fir serves amp_fir.cuh.)
 struct TileCursor {            // monotone walk over the per-utterance tile prefix table
   const int* prefix;
   int b = 0;
@@ -390,180 +391,6 @@ struct TileCursor {            // monotone walk over the per-utterance tile pref
   }
 };
 
-__device__ __forceinline__ void epilogue_role(const TcArgs& a, float* bias_s, const int* prefix, uint32_t bar_accfull0,
-                                              uint32_t bar_accempty0, uint32_t tmem, int nacc, int total_tiles,
-                                              int extra, int q, int lane, int etid) {
-  const int n_tile = a.n_tile, n_tiles = a.n_tiles;
-  const int cg_total = a.Cout >> 3;
-        TileCursor cur{prefix};
-    int it = 0;
-    // the utterance length of the NEXT tile is requested one tile early: a global load is an L2 round trip here
-    int Tin_next = a.Tmax;
-    auto ahead = [&](int w) {
-      if (w >= total_tiles || !a.lengths) return;
-      TileCursor c2 = cur;
-      int b, t0, nt;
-      c2.locate(w, n_tiles, b, t0, nt);
-      Tin_next = __ldg(a.lengths + b) * a.rate;
-    };
-    ahead(blockIdx.x);
-    for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++it) {
-      int b, t0, nt;
-      cur.locate(w, n_tiles, b, t0, nt);
-      const int Tin = Tin_next;
-      ahead(w + gridDim.x);
-      const int T = Tin + extra;
-      const int as = (nacc == 2) ? (it & 1) : 0;
-      const int ause = (nacc == 2) ? (it >> 1) : it;
-      float* bs = bias_s + as * 256;
-      const int cgn0 = nt * (n_tile >> 3);                              // first column group of this tile
-      if (a.bias_b || n_tiles > 1 || it < nacc) {                       // bias row changes with (b, nt) only
-        asm volatile("bar.sync 1, 128;" ::: "memory");                  // previous user of bias_s[as] is done
-        for (int i = etid; i < n_tile; i += 128) {
-          int co = nt * n_tile + i;
-          float v = 0.f;
-          if (co < a.Cout) {
-            if (a.up) co %= a.cphase;
-            v = __ldg(a.bias + co);
-            if (a.bias_b) v += __ldg(a.bias_b + (size_t)b * a.bias_b_stride + co);
-          }
-          bs[i] = v;
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-      }
-      const int gpp = a.up ? (a.cphase >> 3) : cg_total;               // channel groups per output row set
-      const size_t ubase = (size_t)b * gpp * a.Tstride * 8;            // this utterance's block
-      const __nv_bfloat16* resid = a.resid ? a.resid + ubase : nullptr;
-      const __nv_bfloat16* accin = a.acc_in ? a.acc_in + ubase : nullptr;
-      __nv_bfloat16* outp = a.out + ubase;
-      const int ng = min(n_tile >> 3, cg_total - cgn0);                 // valid column groups
-      const int gstride = a.Tstride * 8;                                // elements between channel groups
-      if ((resid || accin) && a.up == 0) {
-        // warm L2 with this tile's residual / running-sum rows while its MMAs are still running
-#pragma unroll 1
-        for (int mb = 0; mb < 2; ++mb) {
-          const int t = t0 + mb * 128 + q * 32 + lane;
-          if (t >= T) continue;
-          int o = cgn0 * gstride + t * 8;
-#pragma unroll 1
-          for (int g = 0; g < ng; ++g, o += gstride) {
-            if (resid) asm volatile("prefetch.global.L2 [%0];" ::"l"(resid + o));
-            if (accin) asm volatile("prefetch.global.L2 [%0];" ::"l"(accin + o));
-          }
-        }
-      }
-      // only one warp polls the accumulator-full mbarrier; the rest sleep on a hardware barrier
-      if (q == 0) mbar_wait_relaxed((bar_accfull0 + 8 * as), ause & 1, 300);
-      asm volatile("bar.sync 2, 128;" ::: "memory");
-      tc_fence_after();
-      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * n_tile);
-      const float rdiv = 1.0f / a.div;
-#pragma unroll 1
-      for (int mb = 0; mb < 2; ++mb) {
-        const int t = t0 + mb * 128 + q * 32 + lane;
-#pragma unroll 1
-        for (int cb0 = 0; cb0 < n_tile; cb0 += 16) {              // 16 accumulator columns = 2 channel groups
-          const int ngrp = min(2, ng - (cb0 >> 3));               // live channel groups in this step
-          if (ngrp <= 0) break;                                    // warp-uniform
-          // element offsets: >= 0 live, -1 skip, <= -2 store zeros at -(off+2)
-          int off[2];
-          uint4 rr[2], qq[2];
-          if (a.up) {                                              // phase scatter of ConvTranspose1d
-#pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-              off[kk] = -1;
-              if (kk >= ngrp) continue;
-              const int cgn = cgn0 + (cb0 >> 3) + kk;
-              const int r = cgn / gpp, cg = cgn - r * gpp;
-              const int to = t * a.up + r - a.pad;
-              if (t < T && to >= 0 && to < Tin * a.up) off[kk] = cg * gstride + to * 8;
-            }
-          } else {
-            const int o0 = (cgn0 + (cb0 >> 3)) * gstride + t * 8;
-            const int code = (t >= a.Tmax || t < a.st_lo || t >= a.st_hi) ? 0 : (t < T ? 1 : 2);
-#pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-              const int o = o0 + kk * gstride;
-              off[kk] = (kk >= ngrp || code == 0) ? -1 : (code == 1 ? o : -2 - o);
-            }
-          }
-          if (resid) {
-#pragma unroll
-            for (int kk = 0; kk < 2; ++kk)
-              if (off[kk] >= 0) rr[kk] = *reinterpret_cast<const uint4*>(resid + off[kk]);
-          }
-          if (accin) {
-#pragma unroll
-            for (int kk = 0; kk < 2; ++kk)
-              if (off[kk] >= 0) qq[kk] = *reinterpret_cast<const uint4*>(accin + off[kk]);
-          }
-          uint32_t v[16];
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-              : "r"(taddr + (uint32_t)(mb * n_tile + cb0)));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int kk = 0; kk < 2; ++kk) {
-            const int ox = off[kk];
-            if (ox == -1) continue;
-            uint4 o = make_uint4(0, 0, 0, 0);
-            if (ox >= 0) {
-              float f[8];
-              const float4 b0 = *reinterpret_cast<const float4*>(bs + cb0 + kk * 8);
-              const float4 b1 = *reinterpret_cast<const float4*>(bs + cb0 + kk * 8 + 4);
-              f[0] = __uint_as_float(v[kk * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[kk * 8 + 1]) + b0.y;
-              f[2] = __uint_as_float(v[kk * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[kk * 8 + 3]) + b0.w;
-              f[4] = __uint_as_float(v[kk * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[kk * 8 + 5]) + b1.y;
-              f[6] = __uint_as_float(v[kk * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[kk * 8 + 7]) + b1.w;
-              if (resid) {
-                const uint32_t rw[4] = {rr[kk].x, rr[kk].y, rr[kk].z, rr[kk].w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  f[2 * e] += __uint_as_float(rw[e] << 16);
-                  f[2 * e + 1] += __uint_as_float(rw[e] & 0xffff0000u);
-                }
-              }
-              if (accin) {
-                const uint32_t qw[4] = {qq[kk].x, qq[kk].y, qq[kk].z, qq[kk].w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  f[2 * e] += __uint_as_float(qw[e] << 16);
-                  f[2 * e + 1] += __uint_as_float(qw[e] & 0xffff0000u);
-                }
-              }
-              if (a.div != 1.0f) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] *= rdiv;
-              }
-              __nv_bfloat162 p0 = __floats2bfloat162_rn(f[0], f[1]), p1 = __floats2bfloat162_rn(f[2], f[3]);
-              __nv_bfloat162 p2 = __floats2bfloat162_rn(f[4], f[5]), p3 = __floats2bfloat162_rn(f[6], f[7]);
-              o = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
-                             *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
-            }
-            *reinterpret_cast<uint4*>(outp + (ox >= 0 ? ox : -(ox + 2))) = o;
-          }
-        }
-      }
-      // accumulator stage can be overwritten by the MMAs of tile it + nacc
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive((bar_accempty0 + 8 * as));
-      // un-activated consumers (ConvTranspose1d) read one row past the end: keep rows [T, T+8) zero
-      // when the utterance ends exactly on this tile's boundary (otherwise they were zeroed above)
-      if (a.up == 0 && T == t0 + M_TILE && T < a.Tmax && T < a.st_hi && q == 0) {
-        const int ngr = min(n_tile >> 3, cg_total - nt * (n_tile >> 3));
-        for (int i = lane; i < ngr * 8; i += 32) {
-          const int g = i >> 3, r = T + (i & 7);
-          if (r < a.Tmax)
-            *reinterpret_cast<uint4*>(a.out + (((size_t)b * cg_total + nt * (n_tile >> 3) + g) * a.Tstride + r) * 8) =
-                make_uint4(0, 0, 0, 0);
-        }
-      }
-    }
-  }
-
 __device__ __forceinline__ u64 add2(u64 a, u64 b) {
   u64 d;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
@@ -572,7 +399,7 @@ __device__ __forceinline__ u64 add2(u64 a, u64 b) {
 
 // Lean conv-mode epilogue (no ConvTranspose scatter, one column tile): TMEM -> +bias(+cond) (+resid) (+sum) (x1/div)
 // -> bf16 -> 16-byte stores.  32 accumulator columns per step with the residual / running-sum rows of the step
-// already in flight when the TMEM load is issued; packed f32x2 arithmetic.  Same store rules as epilogue_role.
+// already in flight when the TMEM load is issued; packed f32x2 arithmetic.
 template <int NCOL, bool HAS_R, bool HAS_Q>
 __device__ __forceinline__ void epi_step(const TcArgs& a, const float* bs, uint32_t taddr, int cb0, int ngs, int code,
                                          const __nv_bfloat16* resid, const __nv_bfloat16* accin, __nv_bfloat16* outp,
@@ -964,7 +791,7 @@ __device__ __forceinline__ void epilogue_pipe(const TcArgs& a, float* bias_s, ui
 
 // ------------------------------------------------------------------------------ ConvTranspose1d epilogue
 // Phase scatter of the (k/u)-tap implicit GEMM (models.py:157-163,232-236): accumulator column n = r*cphase + co holds
-// output time q*up + r - pad of channel co, q = the row's input time.  ncu on the generic epilogue_role showed these
+// output time q*up + r - pad of channel co, q = the row's input time.  ncu on the generic first-generation epilogue showed these
 // launches idle on every pipe (issue 22 %, DRAM 16 %) behind ONE serial chain: ~2100 instructions per epilogue warp and
 // tile (an integer division per column group, 16-column steps).  Here: 32 columns per TMEM load, phase / channel-group
 // counters instead of divisions, packed adds, the next tile's utterance length requested a tile early.
