@@ -201,3 +201,23 @@ def test_utterance_sharding_world_size_2_gloo(tmp_path):
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "GLOO_OK" in r.stdout
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): exactly one JSON line on stdout with the
+    contract's keys, the same metric / unit / workload naming as the GPU arm, and no GPU work claimed."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--workload", "utt6p7s"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["metric"] == "bigvgan_decode_audio_seconds_per_second"
+    assert j["unit"] == "audio-s/s" and j["higher_is_better"] is True and j["gpu_launches"] == 0
+    assert j["config"]["workload"] == "utt6p7s" and j["value"] > 0
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
+    assert j["e2e"] == {"value": j["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
