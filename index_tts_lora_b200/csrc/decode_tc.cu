@@ -610,7 +610,8 @@ static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, cons
     // Worth it unless the layer is bound by the MMA issue thread itself: narrow layers (small N, A-operand-fetch-bound
     // MMAs of ~50 cycles whatever N) with many taps got slower with 4-8 more MMAs and two more hand-shakes per chunk
     // (per-launch events, profiles/r01_rmma_ab.txt): threshold = 36 conv MMAs per tile.
-    const bool rmma_pays = cw.Cin >= 192 || L.nch * cw.K * 4 <= 36;
+    static const int rmma_max_mmas = [] { const char* e = getenv("BVG_RMMA_MAX_MMAS"); return e ? atoi(e) : 36; }();
+    const bool rmma_pays = cw.Cin >= 192 || L.nch * cw.K * 4 <= rmma_max_mmas;
     if (rmma_on && rmma_pays && !q.up && L.idw && (q.resid || q.acc_in)) {
       TcPlan* t = p ? static_cast<TcPlan*>(p->tc) : nullptr;
       rc = 0;
