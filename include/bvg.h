@@ -160,8 +160,12 @@ int bvg_shard_connect_ptr(bvg_plan* plan, int side, void* ws0, void* ws1, void* 
  * (f_end - f_begin) * prod(upsample_rates) samples to wav_out. */
 int bvg_shard_run(bvg_plan* plan, int phase, const void* latent, int latent_dtype, const float* spk_emb,
                   void* wav_out, int wav_dtype, int epoch, int wait, void* stream);
-/* 0 = fine, 1/2 = timed out waiting for the left/right neighbour (synchronises the device) */
+/* 0 = fine, 1/2 = a phase timed out (~4 s) waiting for the left/right neighbour's halo rows; the waveform of that
+ * decode is then invalid.  Reads a mapped host word: no device access, no synchronisation — the word is final once
+ * the stream the phases ran on has been synchronised.  Every later bvg_shard_run fails with BVG_ERR_STATE until
+ * bvg_shard_clear_error (which returns the code it cleared). */
 int bvg_shard_error(bvg_plan* plan);
+int bvg_shard_clear_error(bvg_plan* plan);
 
 /* Number of latent frames of context each side that makes bvg_decode_shard exact
  * (receptive field of the generator in latent frames, rounded up). */

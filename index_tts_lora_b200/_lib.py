@@ -75,6 +75,7 @@ SYMBOLS = {
     "bvg_shard_connect_ptr": (_I, [_P, _I, _P, _P, _P]),
     "bvg_shard_run": (_I, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _P]),
     "bvg_shard_error": (_I, [_P]),
+    "bvg_shard_clear_error": (_I, [_P]),
     "bvg_plan_workspace_bytes": (_L, [_P]),
     "bvg_plan_last_launches": (_I, [_P]),
     "bvg_plan_set_profiling": (_I, [_P, _I]),

@@ -267,8 +267,8 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR_D2EMPTY(h));
-      if (h == 0 && !(a.dbg & 16)) mbar_wait(BAR_ZEMPTY(cx.zs), ((cx.n / NZF) & 1) ^ 1);   // conv MMAs of this z slot's previous chunk retired
-      if (a.dbg & 64) return;
+      if (h == 0 && !BVG_DBGBIT(a, 16)) mbar_wait(BAR_ZEMPTY(cx.zs), ((cx.n / NZF) & 1) ^ 1);   // conv MMAs of this z slot's previous chunk retired
+      if (BVG_DBGBIT(a, 64)) return;
       const float hbf = -cx.nhbf;
 #pragma unroll
       for (int j = 0; j < 12; ++j) {
@@ -305,7 +305,7 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
 #pragma unroll
       for (int p = 0; p < 12; ++p) {
         if (2 * p >= cw) break;
-        if (a.dbg & 32) { sw[p] = v[p]; continue; }
+        if (BVG_DBGBIT(a, 32)) { sw[p] = v[p]; continue; }
         // s' = u + nhb*cos(a2*u) on two consecutive up-sampled positions -> one fp16x2 TMEM column (even position low)
         const u64 u = pk(__uint_as_float(v[2 * p]), __uint_as_float(v[2 * p + 1]));
         float t0f, t1f, s0, s1;
@@ -389,7 +389,7 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
 #pragma unroll 1
           for (int j = 0; j < 16; ++j) {
             const int ts = t0 - hc + (j >> 2) * S - 7, grp = c * 4 + (j & 3);
-            if (ts >= 0 && ts + XB <= a.Tmax && grp < a.xgroups && !(a.dbg & 128))
+            if (ts >= 0 && ts + XB <= a.Tmax && grp < a.xgroups && !BVG_DBGBIT(a, 128))
               bulk_load(dst + j * (XB * 16), a.xin + (((size_t)b * a.xgroups + grp) * a.Tmax + ts) * 8, XB * 16, BAR_XFULL(xs));
             else
               tma_load_4d(dst + j * (XB * 16), &tmx, 0, ts, grp, b, BAR_XFULL(xs));
@@ -432,7 +432,7 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
             const int b0 = h == 0 ? 0 : NB0, nb = h == 0 ? NB0 : NB1;
 #pragma unroll
             for (int i = 0; i < nb; ++i) {
-              if ((a.dbg & 256) && i > 0) break;          // timing experiments only
+              if (BVG_DBGBIT(a, 256) && i > 0) break;          // timing experiments only
               const uint32_t td = tmem + TM_D1 + (uint32_t)(h * 96 + i * 16);
               umma_bf16(td, hiA | (a0 + (b0 + i) * 8), bhi, idesc_up, 0u);
               umma_bf16(td, hiA | (a0 + (b0 + i) * 8), blo, idesc_up, 1u);
@@ -456,7 +456,7 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
             const int z0 = h == 0 ? 0 : NZ0, nz = h == 0 ? NZ0 : NZ1;
 #pragma unroll
             for (int i = 0; i < nz; ++i) {
-              if ((a.dbg & 512) && i > 0) break;          // timing experiments only
+              if (BVG_DBGBIT(a, 512) && i > 0) break;          // timing experiments only
               const int r0 = (16 * (z0 + i) < S - 16) ? 16 * (z0 + i) : S - 16;
 #pragma unroll
               for (int ks = 0; ks < 3; ++ks)
@@ -495,7 +495,7 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
               for (int tj = 0; tj < taps; ++tj) {
                 const uint32_t a0 = aU + (uint32_t)((s * tps + tj) * a.dil);
                 const uint32_t b0 = wU + (uint32_t)tj * tileU;
-                if (a.dbg & 4) continue;                 // timing experiments only
+                if (BVG_DBGBIT(a, 4)) continue;                 // timing experiments only
                 umma_bf16(tm, hiA | a0, hiB | b0, idesc, accflag);
                 umma_bf16(tm, hiA | (a0 + ksA), hiB | (b0 + ksB), idesc, 1u);
                 umma_bf16(tm + n_tile, hiA | (a0 + 128), hiB | b0, idesc, accflag);

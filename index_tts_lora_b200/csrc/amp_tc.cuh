@@ -534,7 +534,7 @@ __device__ __forceinline__ void epilogue_fir_t(const TcArgs& a, float* bias_s, c
     tc_fence_after();
     const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * n_tile);
 #pragma unroll 1
-    for (int mb = 0; mb < ((a.dbg & 8) ? 0 : 2); ++mb) {
+    for (int mb = 0; mb < (BVG_DBGBIT(a, 8) ? 0 : 2); ++mb) {
       const int t = t0 + mb * 128 + q * 32 + lane;
       const int code = (t >= a.Tmax || t < a.st_lo || t >= a.st_hi) ? 0 : (t < T ? 1 : 2);
       constexpr int STEP = (HAS_Q || STEPW == 16) ? 16 : 32;   // fewer rows in flight where registers are short
@@ -644,7 +644,7 @@ __device__ __forceinline__ void epi_rows_finish(const uint4* rr, const uint4* qq
       }
       o = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    if (!(a.dbg & 64)) *reinterpret_cast<uint4*>(outp + o0 + kk * gstride) = o;
+    if (!BVG_DBGBIT(a, 64)) *reinterpret_cast<uint4*>(outp + o0 + kk * gstride) = o;
   }
 }
 
@@ -709,7 +709,7 @@ __device__ __forceinline__ void epilogue_pipe_t(const TcArgs& a, float* bias_s, 
     __nv_bfloat16* outp = a.out + ubase;
     // steps: s -> (mb, cs); spm steps per M block
     const int spm = (ng + NG - 1) / NG;
-    const int nst = (a.dbg & 8) ? 0 : 2 * spm;
+    const int nst = BVG_DBGBIT(a, 8) ? 0 : 2 * spm;
     const int tr0 = t0 + q * 32 + lane, tr1 = tr0 + 128;
     const int code0 = (tr0 >= a.Tmax || tr0 < a.st_lo || tr0 >= a.st_hi) ? 0 : (tr0 < T ? 1 : 2);
     const int code1 = (tr1 >= a.Tmax || tr1 < a.st_lo || tr1 >= a.st_hi) ? 0 : (tr1 < T ? 1 : 2);
@@ -718,7 +718,7 @@ __device__ __forceinline__ void epilogue_pipe_t(const TcArgs& a, float* bias_s, 
       if constexpr (NSTREAM > 0) {
         if (s < nst) {
           const int mb = s >= spm ? 1 : 0, cs = s - mb * spm;
-          if ((mb ? code1 : code0) == 1 && !(a.dbg & 32)) {
+          if ((mb ? code1 : code0) == 1 && !BVG_DBGBIT(a, 32)) {
             const int o0 = cs * NG * gstride + (mb ? tr1 : tr0) * 8, ngs = ng - cs * NG, r = s % LA;
 #pragma unroll
             for (int kk = 0; kk < NG; ++kk) {          // dead groups re-read the last live one
@@ -995,7 +995,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
       // C = 48, second chunk: kg 2-3), whose warps idle, are spread over all four schedulers instead of leaving one
       // scheduler empty and the other three issue-bound.
       // Measured: with no idle groups (C a multiple of 32) the transposed assignment is the faster one by ~5 %.
-      const bool spread = (a.dbg & 256) ? false : ((a.dbg & 512) ? true : (a.Cin & 31) != 0);
+      const bool spread = BVG_DBGBIT(a, 256) ? false : (BVG_DBGBIT(a, 512) ? true : (a.Cin & 31) != 0);
       const int kg = spread ? (warp >> 2) : (warp & 3), wq = spread ? (warp & 3) : (warp >> 2);
       const int g = lane >> 2, p = lane & 3;
       const int ZW = M_TILE + 2 * hc;
@@ -1127,7 +1127,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
           for (int c = 0; c < NCH; ++c) {
             for (int s = 0; s < spc; ++s) {
               const int taps = min(tps, a.K - s * tps);
-              const uint32_t bytes = (a.dbg & 2) ? 16u : (uint32_t)(taps * tile_bytes);
+              const uint32_t bytes = BVG_DBGBIT(a, 2) ? 16u : (uint32_t)(taps * tile_bytes);
               mbar_wait_relaxed(BAR_WEMPTY(stage), phase ^ 1, 300);
               mbar_expect_tx(BAR_WFULL(stage), bytes);
               bulk_load(s_base + OFF_W + stage * W_STAGE_BYTES, src, bytes, BAR_WFULL(stage));
@@ -1178,7 +1178,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
         const uint32_t ring0 = (ACT ? (s_base + OFF_Z) : (s_base + OFF_X + (X_LEAD - a.lead) * 16)) >> 4;
         const uint32_t ringU = (ACT ? Z_BUF_BYTES : X_BUF_BYTES) >> 4;
         const uint32_t barF = ACT ? BAR_ZFULL(0) : BAR_XFULL(0), barE = ACT ? BAR_ZEMPTY(0) : BAR_XEMPTY(0);
-        const bool lazy = ACT && a.Cin <= 96 && !(a.dbg & 4);
+        const bool lazy = ACT && a.Cin <= 96 && !BVG_DBGBIT(a, 4);
         const u64 hiR = make_sdesc(0, M_TILE * 16, 128);    // residual slot: 256 rows per 8-channel group
         int stage = 0, phase = 0, rb = 0, rph = 0, it = 0, rr = 0, rrph = 0;
         for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++it) {
@@ -1202,7 +1202,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
                 const uint32_t a0 = aU + (uint32_t)((s * tps + tj) * a.dil);
                 const uint32_t b0 = wU + (uint32_t)tj * tileU;
                 umma_bf16_e(leader, tm, hiA | a0, hiB | b0, idesc, accflag);
-                if (!(a.dbg & 1)) {
+                if (!BVG_DBGBIT(a, 1)) {
                   umma_bf16_e(leader, tm, hiA | (a0 + ksA), hiB | (b0 + ksB), idesc, 1u);
                   umma_bf16_e(leader, tm + n_tile, hiA | (a0 + 128), hiB | b0, idesc, accflag);
                   umma_bf16_e(leader, tm + n_tile, hiA | (a0 + 128 + ksA), hiB | (b0 + ksB), idesc, 1u);

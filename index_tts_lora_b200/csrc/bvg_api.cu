@@ -7,7 +7,9 @@
 #include <string.h>
 
 #include <map>
+#include <mutex>
 #include <string>
+#include <tuple>
 #include <type_traits>
 
 #include "kernels_f32.cuh"
@@ -29,6 +31,21 @@ int fail(int status, const char* fmt, ...) {
   va_end(ap);
   last_error() = buf;
   return status;
+}
+
+cudaError_t func_attr_once(const void* fn, cudaFuncAttribute attr, int value) {
+  static std::mutex mu;
+  static std::map<std::tuple<const void*, int, int>, int> done;   // (function, attribute, device) -> value set
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(mu);
+  auto key = std::make_tuple(fn, (int)attr, dev);
+  auto it = done.find(key);
+  if (it != done.end() && it->second == value) return cudaSuccess;
+  e = cudaFuncSetAttribute(fn, attr, value);
+  if (e == cudaSuccess) done[key] = value;
+  return e;
 }
 
 static int dev_alloc(bvg_plan* p, void** out, size_t bytes) {
@@ -60,11 +77,7 @@ static int launch_conv(const ConvArgs& a, int B, const Ctx& c) {
   const int ZW = TT + 2 * hc, SW = 2 * ZW + 12, XW = ZW + 12;
   const size_t smem = sizeof(float) * (size_t)(CK * ZW + CK * K * COB + (ACT ? CK * (SW + XW) : 0));
   auto kern = k_conv_f32<K, ACT, TY, NC, NT, XL, FAST>;
-  static bool attr_set = false;   // per template instance
-  if (!attr_set) {
-    BVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
-  }
+  BVG_CUDA(func_attr_once((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   dim3 grid(ceil_div(a.Tmax, TT), ceil_div(a.Cout, COB), B);
   double fl, by;
   conv_cost(c, a, K, &fl, &by);
@@ -101,11 +114,7 @@ static int launch_convtr(const ConvTrArgs& a, int B, const Ctx& c) {
   const int QW = TT / a.U + a.KK / a.U + 2;
   const size_t smem = sizeof(float) * (size_t)(CK * QW + CK * a.KK * COB);
   auto kern = k_convtr_f32<TY, NC, NT, BLK>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    BVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_set = true;
-  }
+  BVG_CUDA(func_attr_once((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   dim3 grid(ceil_div(a.Tmax_out, TT), ceil_div(a.Cout, COB), B);
   const double in_samples = (c.p ? c.p->cur_sum_frames : 0.0) * a.rate_out / a.U;
   prof_begin(c.p, st, c.cls, 2.0 * a.Cin * a.Cout * a.KK * in_samples,
@@ -138,12 +147,27 @@ static int need(const TensorMap& tm, const std::string& name, std::initializer_l
   const bvg_tensor_desc* d = tm.get(name);
   if (!d) return fail(BVG_ERR_ARG, "missing tensor '%s'", name.c_str());
   if (d->dtype != BVG_F32) return fail(BVG_ERR_ARG, "tensor '%s' must be fp32", name.c_str());
-  int64_t have = 1, want = 1;
-  for (int i = 0; i < d->ndim; ++i) have *= d->shape[i];
-  for (int64_t s : shape) want *= s;
-  if (have != want)
-    return fail(BVG_ERR_ARG, "tensor '%s' has %lld elements, expected %lld", name.c_str(),
-                (long long)have, (long long)want);
+  // full shape, not just the element count: a ConvTranspose1d weight handed over as [Cout,Cin,K] instead of
+  // [Cin,Cout,K] would otherwise load silently and decode garbage.  Leading / trailing unit dims are tolerated
+  // (filters are [1,1,12] in the state dict, alpha / beta are [C]).
+  auto squeeze = [](const int64_t* s, int n, int64_t* out) {
+    int m = 0;
+    for (int i = 0; i < n; ++i) if (s[i] != 1) out[m++] = s[i];
+    return m;
+  };
+  int64_t hs[8], wsq[8], wraw[8];
+  int nw = 0;
+  for (int64_t v : shape) if (nw < 8) wraw[nw++] = v;
+  if (d->ndim < 0 || d->ndim > 4) return fail(BVG_ERR_ARG, "tensor '%s': ndim %d", name.c_str(), d->ndim);
+  const int nh = squeeze(d->shape, d->ndim, hs), nq = squeeze(wraw, nw, wsq);
+  bool same = nh == nq;
+  for (int i = 0; same && i < nh; ++i) same = hs[i] == wsq[i];
+  if (!same) {
+    std::string have, want;
+    for (int i = 0; i < d->ndim; ++i) have += (i ? "," : "") + std::to_string((long long)d->shape[i]);
+    for (int i = 0; i < nw; ++i) want += (i ? "," : "") + std::to_string((long long)wraw[i]);
+    return fail(BVG_ERR_ARG, "tensor '%s' has shape [%s], expected [%s]", name.c_str(), have.c_str(), want.c_str());
+  }
   *out = reinterpret_cast<const float*>(d->data);
   return 0;
 }
@@ -195,6 +219,10 @@ static int load_act(bvg_plan* p, const TensorMap& tm, const std::string& prefix,
 // ------------------------------------------------------------------------------ workspace
 static int ensure_ws(bvg_plan* p, size_t bytes_per_buf) {
   if (bytes_per_buf <= p->ws_bytes) return 0;
+  if (tc_shard_pins_ws(p))
+    return fail(BVG_ERR_STATE, "this decode needs a larger workspace (%zu B per buffer, have %zu), but the workspace is "
+                "exported to the neighbouring GPUs of a time-split decode: call bvg_shard_setup again afterwards, or use "
+                "a separate plan", bytes_per_buf, p->ws_bytes);
   BVG_CUDA(cudaDeviceSynchronize());
   for (int i = 0; i < 4; ++i) {
     if (p->ws[i]) BVG_CUDA(cudaFree(p->ws[i]));
@@ -399,6 +427,17 @@ static int check_device(int device, int* sm_count) {
                 prop.major, prop.minor);
   if (sm_count) *sm_count = prop.multiProcessorCount;
   return 0;
+}
+
+static int check_device_cached(int device) {
+  static std::mutex mu;
+  static std::map<int, int> ok;           // device -> status of check_device
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = ok.find(device);
+  if (it != ok.end() && it->second == 0) return 0;
+  const int rc = check_device(device, nullptr);
+  if (rc == 0) ok[device] = 0;
+  return rc;
 }
 
 }  // namespace bvg
@@ -663,7 +702,8 @@ int bvg_shard_run(bvg_plan* p, int phase, const void* latent, int latent_dtype, 
   BVG_CUDA(cudaSetDevice(p->device));
   return tc_shard_run(p, phase, latent, latent_dtype, spk_emb, wav_out, wav_dtype, epoch, wait, (cudaStream_t)stream);
 }
-int bvg_shard_error(bvg_plan* p) { return p ? tc_shard_error(p) : -1; }
+int bvg_shard_error(bvg_plan* p) { return p ? tc_shard_error(p, 0) : -1; }
+int bvg_shard_clear_error(bvg_plan* p) { return p ? tc_shard_error(p, 1) : -1; }
 
 int64_t bvg_plan_workspace_bytes(const bvg_plan* p) {
   return p ? (int64_t)(4 * p->ws_bytes + tc_plan_workspace_bytes(p)) : -1;
@@ -706,43 +746,42 @@ int bvg_plan_read_profile(bvg_plan* p, bvg_profile* out) {
 }
 
 // ------------------------------------------------------------------------------ per-op
-static int tmp_snake(const float* alpha, const float* beta, int C, int logscale, cudaStream_t st,
-                     float** a, float** invb) {
-  BVG_CUDA(cudaMallocAsync((void**)a, C * sizeof(float), st));
-  BVG_CUDA(cudaMallocAsync((void**)invb, C * sizeof(float), st));
-  k_snake_params<<<ceil_div(C, 128), 128, 0, st>>>(alpha, beta, *a, *invb, C, logscale);
-  BVG_CUDA(cudaGetLastError());
-  return 0;
-}
+// stream-ordered temporaries of the per-op entry points: freed on every exit path
+struct AsyncTmp {
+  cudaStream_t st;
+  void* ptrs[8];
+  int n = 0;
+  explicit AsyncTmp(cudaStream_t s) : st(s) {}
+  cudaError_t alloc(void** out, size_t bytes) {
+    if (n >= 8) return cudaErrorMemoryAllocation;
+    cudaError_t e = cudaMallocAsync(out, bytes ? bytes : 4, st);
+    if (e == cudaSuccess) ptrs[n++] = *out;
+    return e;
+  }
+  ~AsyncTmp() { for (int i = 0; i < n; ++i) cudaFreeAsync(ptrs[i], st); }
+};
 
 int bvg_activation1d(const void* x, void* y, int dtype, int B, int C, int T, const float* up_filter,
                      const float* down_filter, const float* alpha, const float* beta, int logscale,
                      void* stream) {
   BVG_REQUIRE(x && y && up_filter && down_filter && alpha && beta, "bvg_activation1d: null argument");
   BVG_REQUIRE(B >= 1 && C >= 1 && T >= 1 && B <= 65535 && C <= 65535, "bvg_activation1d: bad shape");
+  BVG_REQUIRE(dtype == BVG_F32 || dtype == BVG_BF16 || dtype == BVG_F16, "bvg_activation1d: dtype %d", dtype);
   int dev, rc;
   BVG_CUDA(cudaGetDevice(&dev));
-  if ((rc = check_device(dev, nullptr))) return rc;
+  if ((rc = check_device_cached(dev))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  ActParams ap;
-  BVG_CUDA(cudaMemcpyAsync(ap.up, up_filter, 12 * sizeof(float), cudaMemcpyDeviceToHost, st));
-  BVG_CUDA(cudaMemcpyAsync(ap.dn, down_filter, 12 * sizeof(float), cudaMemcpyDeviceToHost, st));
-  float *a, *invb;
-  if ((rc = tmp_snake(alpha, beta, C, logscale, st, &a, &invb))) return rc;
-  BVG_CUDA(cudaStreamSynchronize(st));  // taps must be on the host before they travel by value
-  ap.a = a; ap.invb = invb;
+  // one asynchronous launch on the caller's stream: no host copies, no synchronisation, graph-capturable
   dim3 grid(ceil_div(ceil_div(T, 4), 256), C, B);
   if (dtype == BVG_F32)
-    k_act1d<float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, C, T, ap);
+    k_act1d<float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, C, T, up_filter, down_filter, alpha, beta, logscale);
   else if (dtype == BVG_BF16)
-    k_act1d<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, C, T, ap);
-  else if (dtype == BVG_F16)
-    k_act1d<__half><<<grid, 256, 0, st>>>((const __half*)x, (__half*)y, C, T, ap);
+    k_act1d<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, C, T, up_filter,
+                                                 down_filter, alpha, beta, logscale);
   else
-    return fail(BVG_ERR_ARG, "bvg_activation1d: dtype %d", dtype);
+    k_act1d<__half><<<grid, 256, 0, st>>>((const __half*)x, (__half*)y, C, T, up_filter, down_filter, alpha, beta,
+                                          logscale);
   BVG_CUDA(cudaGetLastError());
-  BVG_CUDA(cudaFreeAsync(a, st));
-  BVG_CUDA(cudaFreeAsync(invb, st));
   return 0;
 }
 
@@ -756,22 +795,28 @@ int bvg_amp_layer(const float* x, float* y, const float* resid, int B, int C_in,
               "bvg_amp_layer: bad shape (C_in must be a multiple of 8)");
   int dev, rc;
   BVG_CUDA(cudaGetDevice(&dev));
-  if ((rc = check_device(dev, nullptr))) return rc;
+  if ((rc = check_device_cached(dev))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (precision == BVG_PREC_BF16)
     return tc_amp_layer(x, y, resid, B, C_in, C_out, T, w, bias, k, dilation, act, up_filter,
                         down_filter, alpha, beta, logscale, st);
   BVG_REQUIRE(precision == BVG_PREC_F32, "bvg_amp_layer: unknown precision");
+  // layer-level TEST entry point (bvg.h): packs the weights per call and reads the taps back to the host, so it
+  // synchronises the stream once; the decode path packs at load time and never does
+  AsyncTmp tmp(st);
   float *wp, *a = nullptr, *invb = nullptr;
   const size_t n = (size_t)C_out * C_in * k;
-  BVG_CUDA(cudaMallocAsync((void**)&wp, n * sizeof(float), st));
+  BVG_CUDA(tmp.alloc((void**)&wp, n * sizeof(float)));
   k_pack_conv_w<<<(int)std::min<size_t>((n + 255) / 256, 4096), 256, 0, st>>>(w, wp, C_out, C_in, k);
   BVG_CUDA(cudaGetLastError());
   ConvArgs ca{};
   if (act) {
     BVG_CUDA(cudaMemcpyAsync(ca.act.up, up_filter, 12 * sizeof(float), cudaMemcpyDeviceToHost, st));
     BVG_CUDA(cudaMemcpyAsync(ca.act.dn, down_filter, 12 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if ((rc = tmp_snake(alpha, beta, C_in, logscale, st, &a, &invb))) return rc;
+    BVG_CUDA(tmp.alloc((void**)&a, C_in * sizeof(float)));
+    BVG_CUDA(tmp.alloc((void**)&invb, C_in * sizeof(float)));
+    k_snake_params<<<ceil_div(C_in, 128), 128, 0, st>>>(alpha, beta, a, invb, C_in, logscale);
+    BVG_CUDA(cudaGetLastError());
     BVG_CUDA(cudaStreamSynchronize(st));
     ca.act.a = a; ca.act.invb = invb;
   }
@@ -781,11 +826,7 @@ int bvg_amp_layer(const float* x, float* y, const float* resid, int B, int C_in,
   ca.Cin = C_in; ca.Cout = C_out; ca.dil = dilation;
   ca.lengths = nullptr; ca.rate = 1; ca.Tmax = T;
   Ctx cx{nullptr, st, 0, 4.0};
-  rc = act ? launch_conv_k<true>(k, ca, B, cx) : launch_conv_k<false>(k, ca, B, cx);
-  cudaFreeAsync(wp, st);
-  if (a) cudaFreeAsync(a, st);
-  if (invb) cudaFreeAsync(invb, st);
-  return rc;
+  return act ? launch_conv_k<true>(k, ca, B, cx) : launch_conv_k<false>(k, ca, B, cx);
 }
 
 int bvg_conv_transpose1d(const float* x, float* y, int B, int C_in, int C_out, int T, const float* w,
@@ -799,9 +840,10 @@ int bvg_conv_transpose1d(const float* x, float* y, int B, int C_in, int C_out, i
   cudaStream_t st = (cudaStream_t)stream;
   if (precision != BVG_PREC_F32)
     return fail(BVG_ERR_UNSUPPORTED, "bvg_conv_transpose1d: only the fp32 per-op path is exposed");
+  AsyncTmp tmp(st);
   float* wp;
   const size_t n = (size_t)C_out * C_in * k;
-  BVG_CUDA(cudaMallocAsync((void**)&wp, n * sizeof(float), st));
+  BVG_CUDA(tmp.alloc((void**)&wp, n * sizeof(float)));
   k_pack_convtr_w<<<(int)std::min<size_t>((n + 255) / 256, 4096), 256, 0, st>>>(w, wp, C_in, C_out, k);
   BVG_CUDA(cudaGetLastError());
   ConvTrArgs a{};
@@ -810,9 +852,7 @@ int bvg_conv_transpose1d(const float* x, float* y, int B, int C_in, int C_out, i
   a.Cin = C_in; a.Cout = C_out; a.KK = k; a.U = u;
   a.lengths = nullptr; a.rate_out = u; a.Tmax_out = T * u;
   Ctx cx{nullptr, st, 2, 4.0};
-  rc = launch_convtr<false>(a, B, cx);
-  cudaFreeAsync(wp, st);
-  return rc;
+  return launch_convtr<false>(a, B, cx);
 }
 
 }  // extern "C"

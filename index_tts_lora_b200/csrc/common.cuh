@@ -69,4 +69,16 @@ __device__ __forceinline__ void st_dyn(void* base, size_t idx, int dtype, float 
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Timing knock-outs (BVG_DBG bits) change the arithmetic of the kernels; they exist only in builds made with
+// -DBVG_EXPERIMENTS (tools/), never in the shipped library.
+#ifdef BVG_EXPERIMENTS
+#define BVG_DBGBIT(a, bit) (((a).dbg & (bit)) != 0)
+#else
+#define BVG_DBGBIT(a, bit) false
+#endif
+
+// cudaFuncSetAttribute is per (function, device): a plan per GPU in one process, or a module moved between GPUs,
+// must opt every device in.  Thread-safe; returns a cudaError_t.
+cudaError_t func_attr_once(const void* fn, cudaFuncAttribute attr, int value);
+
 }  // namespace bvg

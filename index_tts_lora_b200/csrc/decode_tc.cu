@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <map>
 #include <tuple>
 #include <vector>
@@ -358,18 +359,20 @@ static int make_map(const void* base, int C, int Tstride, int B, CUtensorMap* ou
   return 0;
 }
 
-static int get_map(TcPlan* t, const void* base, int C, int Tstride, int B, const CUtensorMap** out, int rows = 0,
+// Cached per plan; the map is COPIED out (128 B), so no caller ever holds a reference into the cache, and the cache is
+// only ever emptied between decodes (tc_prepare) — a decode adds ~80 keys per distinct (Tmax, B) shape.
+constexpr size_t kMapCacheMax = 4096;
+static int get_map(TcPlan* t, const void* base, int C, int Tstride, int B, CUtensorMap* out, int rows = 0,
                    int box_rows = BOXR) {
   auto key = std::make_tuple(base, C, Tstride, B, rows, box_rows);
   auto it = t->maps.find(key);
   if (it == t->maps.end()) {
-    if (t->maps.size() > 4096) t->maps.clear();
     CUtensorMap m;
     int rc = make_map(base, C, Tstride, B, &m, rows, box_rows);
     if (rc) return rc;
     it = t->maps.emplace(key, m).first;
   }
-  *out = &it->second;
+  *out = it->second;
   return 0;
 }
 
@@ -399,21 +402,13 @@ template <int L, bool ACT, bool RM, int EPI>
 static int launch_inst_rm(const CUtensorMap& map, const CUtensorMap& mapr, const CUtensorMap& mapq, const TcArgs& a, dim3 grid,
                           cudaStream_t st) {
   auto kern = k_amp_tc<L, ACT, RM, EPI>;
-  static bool attr = false;
-  if (!attr) {
-    BVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
-  }
+  BVG_CUDA(func_attr_once((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   const int smem = smem_bytes(a.nx, a.nz, a.wst);
   if (smem > 227 * 1024) return fail(BVG_ERR_STATE, "k_amp_tc smem plan %d B exceeds 227 KB", smem);
   // Whatever the rings leave of the 228 KB goes to L1, which is what serves the register spills of the 32- / 64-register
   // roles (local memory) and the few global scalars: ask for the smallest carve-out that holds this launch.
-  static int carve = -1;
   const int want = std::min(100, (smem + 1024) * 100 / (228 * 1024) + 1);
-  if (want != carve) {
-    BVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, want));
-    carve = want;
-  }
+  BVG_CUDA(func_attr_once((const void*)kern, cudaFuncAttributePreferredSharedMemoryCarveout, want));
   kern<<<grid, NTHREADS, smem, st>>>(map, mapr, mapq, a);
   BVG_CUDA(cudaGetLastError());
   return 0;
@@ -437,20 +432,16 @@ static int launch_inst(const CUtensorMap& map, const CUtensorMap& mapr, const CU
 template <int NUB>
 static int launch_fir_inst(const CUtensorMap& map, const TcArgs& a, dim3 grid, cudaStream_t st) {
   auto kern = fir::k_amp_fir<NUB>;
-  static bool attr = false;
-  if (!attr) {
-    BVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fir::F_SMEM));
-    attr = true;
-  }
+  BVG_CUDA(func_attr_once((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fir::F_SMEM));
   kern<<<grid, fir::NTHREADS_F, fir::F_SMEM, st>>>(map, a);
   BVG_CUDA(cudaGetLastError());
   return 0;
 }
 
 // narrow activated layers may take k_amp_fir (both FIRs on the tensor cores): opt-in, see bvg_set_tc_fir_max_channels
-static int g_fir_max_c = -1;
+static std::atomic<int> g_fir_max_c{-1};
 int tc_set_fir_max_c(int v) {
-  const int old = g_fir_max_c < 0 ? 0 : g_fir_max_c;
+  const int cur = g_fir_max_c.load(), old = cur < 0 ? 0 : cur;
   g_fir_max_c = v < 0 ? 0 : v;
   return old;
 }
@@ -464,9 +455,9 @@ static int fir_max_c() {
 
 // Layers with C_in >= this many channels run Activation1d once in k_act_blk and the conv as k_amp_tc<ACT = false>
 // (act_blk.cuh) instead of repeating the activation per column tile inside the fused kernel.  0 = never.
-static int g_split_min_c = -1;
+static std::atomic<int> g_split_min_c{-1};
 int tc_set_split_min_c(int v) {
-  const int old = g_split_min_c < 0 ? kSplitMinCDefault : g_split_min_c;
+  const int cur = g_split_min_c.load(), old = cur < 0 ? kSplitMinCDefault : cur;
   g_split_min_c = v < 0 ? 0 : v;
   return old;
 }
@@ -480,9 +471,9 @@ static int split_min_c() {
 static bool split_layer(int Cin) { return split_min_c() > 0 && Cin >= split_min_c(); }
 
 // Residual / running-sum add by identity MMAs (amp_tc.cuh) on the layers where it pays; off = always in the epilogue.
-static int g_rmma = -1;
+static std::atomic<int> g_rmma{-1};
 int tc_set_residual_mma(int on) {
-  const int old = g_rmma < 0 ? 1 : g_rmma;
+  const int cur = g_rmma.load(), old = cur < 0 ? 1 : cur;
   g_rmma = on ? 1 : 0;
   return old;
 }
@@ -505,11 +496,7 @@ static int launch_act_blk(bvg_plan* p, const ConvW& cw, const ActW* aw, const Tc
   if (units >= (1LL << 31)) return fail(BVG_ERR_UNSUPPORTED, "k_act_blk: %lld work units exceed 2^31", units);
   const int sms = q.sm_count > 0 ? q.sm_count : 148;
   const int smem = AB_WARPS * AB_SMEM_PER_WARP + 8192;   // tail slack: the edge path's clamped reads of unused rows
-  static bool attr = false;
-  if (!attr) {
-    BVG_CUDA(cudaFuncSetAttribute(k_act_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
-  }
+  BVG_CUDA(func_attr_once((const void*)k_act_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid((unsigned)std::min<long long>((units + AB_WARPS - 1) / AB_WARPS, 2LL * sms));
   const double samples = (p ? p->cur_sum_frames : 0.0) * q.rate;
   prof_begin(p, st, q.cls, 0.0, samples * 2.0 * 2.0 * cw.Cin);
@@ -526,15 +513,14 @@ static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, cons
     // split form: z = Activation1d(x) once, then the plain dilated conv over z
     int rc;
     if ((rc = launch_act_blk(p, cw, aw, L, q, st))) return rc;
-    CUtensorMap tmp;
-    const CUtensorMap* zm = &tmp;
+    CUtensorMap zm;
     TcPlan* t = p ? static_cast<TcPlan*>(p->tc) : nullptr;
     if (t) rc = get_map(t, q.zbuf, cw.Cin, q.Tstride, q.B, &zm);
-    else rc = make_map(q.zbuf, cw.Cin, q.Tstride, q.B, &tmp);
+    else rc = make_map(q.zbuf, cw.Cin, q.Tstride, q.B, &zm);
     if (rc) return rc;
     TcLaunch qc = q;
     qc.x = q.zbuf; qc.zbuf = nullptr;
-    return launch_tc(p, *zm, L, cw, nullptr, qc, st);
+    return launch_tc(p, zm, L, cw, nullptr, qc, st);
   }
   TcArgs a{};
   a.wt = L.wt; a.bias = cw.bias; a.bias_b = q.bias_b; a.bias_b_stride = q.bias_b_stride;
@@ -549,22 +535,30 @@ static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, cons
   if (!aw) { a.nx = 3; a.nz = 2; a.wst = 4; }                       // plain conv / ConvTranspose1d: the MMA reads the x ring
   else if (cw.Cin <= 96) { a.nx = 3; a.nz = 3; a.wst = 3; }
   else { a.nx = 2; a.nz = 3; a.wst = 4; }
+#ifdef BVG_EXPERIMENTS
   {
-    static int ov[3] = {-1, -1, -1};      // BVG_RINGS="nx,nz,wst": experiment hook
-    if (ov[0] < 0) {
-      ov[0] = 0;
-      if (const char* e = getenv("BVG_RINGS")) sscanf(e, "%d,%d,%d", &ov[0], &ov[1], &ov[2]);
-    }
-    if (ov[0] > 0) { a.nx = ov[0]; a.nz = ov[1]; a.wst = ov[2]; }
+    // BVG_RINGS="nx,nz,wst": ring-depth experiments; all three fields must parse and stay inside the mbarrier table
+    static const std::tuple<int, int, int> ov = [] {
+      int x = 0, z = 0, w = 0;
+      const char* e = getenv("BVG_RINGS");
+      if (!e || sscanf(e, "%d,%d,%d", &x, &z, &w) != 3 || x < 2 || x > NX_MAX || z < 2 || z > NZ_MAX || w < 2 ||
+          w > W_STAGES_MAX)
+        return std::make_tuple(0, 0, 0);
+      return std::make_tuple(x, z, w);
+    }();
+    if (std::get<0>(ov) > 0) { a.nx = std::get<0>(ov); a.nz = std::get<1>(ov); a.wst = std::get<2>(ov); }
   }
+#endif
   a.Tstride = q.out_tstride ? q.out_tstride : q.Tstride;
   a.lengths = q.d_len; a.rate = q.rate; a.Tmax = q.Tstride;
   a.up = q.up; a.pad = q.pad; a.cphase = q.cphase;
   a.st_lo = q.st_lo; a.st_hi = q.st_hi;
+#ifdef BVG_EXPERIMENTS
   {
     static const int dbg = [] { const char* e = getenv("BVG_DBG"); return e ? atoi(e) : 0; }();
     a.dbg = dbg;
   }
+#endif
   const int hc = q.dil * (cw.K - 1) / 2;
   a.lead = q.up ? cw.K - 1 : hc;
   if (aw) {
@@ -590,23 +584,22 @@ static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, cons
                        cw.Cout <= fir_max_c() && hc <= 32;
   if (use_fir) {
     // x tile = 16 TMA boxes {8 channels, 96 rows} (4 time segments x 4 channel groups)
-    CUtensorMap tmp;
-    const CUtensorMap* fm = &tmp;
+    CUtensorMap fm;
     TcPlan* t = p ? static_cast<TcPlan*>(p->tc) : nullptr;
     if (t) rc = get_map(t, q.x, cw.Cin, q.Tstride, q.B, &fm, 0, fir::XB);
-    else rc = make_map(q.x, cw.Cin, q.Tstride, q.B, &tmp, 0, fir::XB);
+    else rc = make_map(q.x, cw.Cin, q.Tstride, q.B, &fm, 0, fir::XB);
     if (rc) return rc;
     a.wst = fir::W_STAGES_F;
     a.xin = static_cast<const __nv_bfloat16*>(q.x);
     a.xgroups = cw.Cin / 8;
-    rc = (hc <= 16) ? launch_fir_inst<10>(*fm, a, grid, st) : launch_fir_inst<11>(*fm, a, grid, st);
+    rc = (hc <= 16) ? launch_fir_inst<10>(fm, a, grid, st) : launch_fir_inst<11>(fm, a, grid, st);
   } else
   {
     // residual / running-sum add as identity MMAs (D += R x I) instead of loads + adds in the epilogue warps
     const bool rmma_on = residual_mma_on();
-    const CUtensorMap* mr = &map;
-    const CUtensorMap* mq = &map;
     CUtensorMap tmpr, tmpq;
+    const CUtensorMap* mr = &map;       // `map` is the caller's own copy; tmpr / tmpq are ours
+    const CUtensorMap* mq = &map;
     // Worth it unless the layer is bound by the MMA issue thread itself: narrow layers (small N, A-operand-fetch-bound
     // MMAs of ~50 cycles whatever N) with many taps got slower with 4-8 more MMAs and two more hand-shakes per chunk
     // (per-launch events, profiles/r01_rmma_ab.txt): threshold = 36 conv MMAs per tile.
@@ -617,11 +610,11 @@ static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, cons
       rc = 0;
       if (q.resid) {
         mr = &tmpr;
-        rc = t ? get_map(t, q.resid, cw.Cout, a.Tstride, q.B, &mr, 0, 128) : make_map(q.resid, cw.Cout, a.Tstride, q.B, &tmpr, 0, 128);
+        rc = t ? get_map(t, q.resid, cw.Cout, a.Tstride, q.B, &tmpr, 0, 128) : make_map(q.resid, cw.Cout, a.Tstride, q.B, &tmpr, 0, 128);
       }
       if (!rc && q.acc_in) {
         mq = &tmpq;
-        rc = t ? get_map(t, q.acc_in, cw.Cout, a.Tstride, q.B, &mq, q.acc_rows, 128)
+        rc = t ? get_map(t, q.acc_in, cw.Cout, a.Tstride, q.B, &tmpq, q.acc_rows, 128)
                : make_map(q.acc_in, cw.Cout, a.Tstride, q.B, &tmpq, q.acc_rows, 128);
       }
       if (rc) return rc;
@@ -659,6 +652,7 @@ struct StageIO {
 
 static int tc_prepare(bvg_plan* p, TcPlan* t, int B, int Fs) {
   int rc;
+  if (t->maps.size() > kMapCacheMax) t->maps.clear();   // nothing holds a reference between decodes
   size_t max_elems = (size_t)p->C[0] * Fs;
   for (int i = 0; i < p->n_stages; ++i)
     max_elems = std::max(max_elems, (size_t)p->C[i + 1] * Fs * p->rate[i + 1]);
@@ -706,7 +700,7 @@ static int tc_prepare(bvg_plan* p, TcPlan* t, int B, int Fs) {
 static int tc_pre(bvg_plan* p, TcPlan* t, const void* latent, int latent_dtype, __nv_bfloat16* out, int B, int Fs,
                   const int32_t* h_len, const int* d_len, cudaStream_t st) {
   int rc;
-  const CUtensorMap* map;
+  CUtensorMap map;
   dim3 grid(ceil_div(Fs, 128), p->cfg.gpt_dim / 8, B);
   prof_begin(p, st, 2, 0.0, (double)B * Fs * p->cfg.gpt_dim * 6.0);
   k_latent_blk<<<grid, 128, 0, st>>>(latent, latent_dtype, (__nv_bfloat16*)t->lat_blk, p->cfg.gpt_dim, Fs, d_len);
@@ -718,13 +712,13 @@ static int tc_pre(bvg_plan* p, TcPlan* t, const void* latent, int latent_dtype, 
   q.x = t->lat_blk; q.out = out; q.bias_b = p->condb + p->cond_off[0]; q.bias_b_stride = p->cond_total;
   q.dil = 1; q.B = B; q.Tstride = Fs; q.rate = 1; q.d_len = d_len; q.cls = 2;
   q.h_len = h_len; q.sm_count = p->sm_count;
-  return launch_tc(p, *map, t->pre, p->conv_pre, nullptr, q, st);
+  return launch_tc(p, map, t->pre, p->conv_pre, nullptr, q, st);
 }
 
 // one upsampling stage: ConvTranspose1d + cond add, three AMP blocks, mean (models.py:230-245)
 static int tc_stage(bvg_plan* p, TcPlan* t, int i, const StageIO& io, cudaStream_t st) {
   int rc;
-  const CUtensorMap* map;
+  CUtensorMap map;
   const int nk = p->cfg.num_kernels;
   const int B = io.B;
   const int Ci = p->C[i + 1], Ri = p->rate[i + 1], Ti = io.Fs * Ri;
@@ -744,7 +738,7 @@ static int tc_stage(bvg_plan* p, TcPlan* t, int i, const StageIO& io, cudaStream
     qu.bias_b = p->cfg.cond_in_each_up_layer ? p->condb + p->cond_off[i + 1] : nullptr;
     qu.bias_b_stride = p->cond_total;
     if ((rc = get_map(t, io.cur, p->C[i], Tin, B, &map, io.cur_rows))) return rc;
-    if ((rc = launch_tc(p, *map, t->ups[i], cw, nullptr, qu, st))) return rc;
+    if ((rc = launch_tc(p, map, t->ups[i], cw, nullptr, qu, st))) return rc;
   }
   if (nstreams > 1) {
     BVG_CUDA(cudaEventRecord(t->ev_fork, st));
@@ -764,7 +758,7 @@ static int tc_stage(bvg_plan* p, TcPlan* t, int i, const StageIO& io, cudaStream
       qa.h_len = io.h_len; qa.sm_count = p->sm_count;
       qa.zbuf = split_layer(Ci) ? (__nv_bfloat16*)t->zbuf[j % 3] : nullptr;
       if ((rc = get_map(t, xcur, Ci, Ti, B, &map))) return rc;
-      if ((rc = launch_tc(p, *map, t->rb1[n][m], p->rb1[n][m], &p->rba[n][2 * m], qa, sq))) return rc;
+      if ((rc = launch_tc(p, map, t->rb1[n][m], p->rb1[n][m], &p->rba[n][2 * m], qa, sq))) return rc;
 
       const bool last = (m == BVG_MAX_DIL - 1);
       TcLaunch qb;
@@ -784,7 +778,7 @@ static int tc_stage(bvg_plan* p, TcPlan* t, int i, const StageIO& io, cudaStream
         qb.st_hi = (io.st_hi_f >= 0x7fffff) ? 0x7fffffff : io.st_hi_f * Ri;
       }
       if ((rc = get_map(t, xt, Ci, Ti, B, &map))) return rc;
-      if ((rc = launch_tc(p, *map, t->rb2[n][m], p->rb2[n][m], &p->rba[n][2 * m + 1], qb, sq))) return rc;
+      if ((rc = launch_tc(p, map, t->rb2[n][m], p->rb2[n][m], &p->rba[n][2 * m + 1], qb, sq))) return rc;
       if (last && nstreams > 1) BVG_CUDA(cudaEventRecord(t->ev_last[j], sq));
       xcur = xr;
     }
@@ -863,7 +857,11 @@ struct ShardState {
   void* nbr_ws[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // neighbour's ws[0], ws[1]
   int* nbr_flags[2] = {nullptr, nullptr};
   bool nbr_ipc[2] = {false, false};
-  void* exported_ws0 = nullptr;
+  void* exported_ws[2] = {nullptr, nullptr};
+  // error word of the decode in flight (k_halo_wait timeout), in mapped pinned memory: the host reads it without
+  // touching the device, so every decode can check the previous one for free
+  int* h_err = nullptr;
+  int* d_err = nullptr;
 };
 
 static ShardState* shard_of(bvg_plan* p) {
@@ -896,10 +894,22 @@ __global__ void k_halo_wait(const int* flag_l, const int* flag_r, int epoch, int
     long long spins = 0;
     while (*f < epoch) {
       __nanosleep(200);
-      if (++spins > 20000000LL) { *err = 1 + side; return; }   // ~4 s: give up instead of hanging the GPU
+      if (++spins > 20000000LL) {                              // ~4 s: give up instead of hanging the GPU
+        *reinterpret_cast<volatile int*>(err) = 1 + side;
+        __threadfence_system();
+        return;
+      }
     }
   }
   __threadfence_system();
+}
+
+// ws[0..1] are IPC-exported to the neighbours once a shard is set up: an ordinary decode must not re-allocate them
+// under the peers' feet (bvg_api.cu::ensure_ws refuses to grow while this returns true)
+bool tc_shard_pins_ws(const bvg_plan* p) {
+  const TcPlan* t = static_cast<const TcPlan*>(p->tc);
+  const ShardState* s = t ? static_cast<const ShardState*>(t->shard) : nullptr;
+  return s && s->ready;
 }
 
 int tc_shard_setup(bvg_plan* p, const bvg_shard_geom* g, cudaStream_t st) {
@@ -907,6 +917,7 @@ int tc_shard_setup(bvg_plan* p, const bvg_shard_geom* g, cudaStream_t st) {
   if (!t) return fail(BVG_ERR_STATE, "shard setup: weights not loaded");
   if (!t->shard) t->shard = new ShardState();
   ShardState* s = static_cast<ShardState*>(t->shard);
+  s->ready = false;                      // a new geometry may grow the workspace (and must then be re-exported)
   const int S = p->n_stages, own = g->f_end - g->f_begin;
   BVG_REQUIRE(g->f_begin >= 0 && own > 0 && g->f_end <= g->f_total, "bad shard range");
   BVG_REQUIRE(g->own_max >= own, "own_max smaller than this shard");
@@ -943,9 +954,15 @@ int tc_shard_setup(bvg_plan* p, const bvg_shard_geom* g, cudaStream_t st) {
     BVG_CUDA(cudaMalloc((void**)&s->flags, sizeof(int) * 64));
     BVG_CUDA(cudaMemsetAsync(s->flags, 0, sizeof(int) * 64, st));
   }
+  if (!s->h_err) {
+    BVG_CUDA(cudaHostAlloc((void**)&s->h_err, sizeof(int), cudaHostAllocMapped));
+    *s->h_err = 0;
+    BVG_CUDA(cudaHostGetDevicePointer((void**)&s->d_err, s->h_err, 0));
+  }
   BVG_CUDA(cudaMemcpyAsync(s->d_win, s->h_win, sizeof(int) * (kMaxStages + 2), cudaMemcpyHostToDevice, st));
   BVG_CUDA(cudaStreamSynchronize(st));
-  s->exported_ws0 = p->ws[0];
+  s->exported_ws[0] = p->ws[0];
+  s->exported_ws[1] = p->ws[1];
   s->ready = true;
   return 0;
 }
@@ -1004,6 +1021,7 @@ void tc_shard_free(TcPlan* t) {
     }
   if (s->d_win) cudaFree(s->d_win);
   if (s->flags) cudaFree(s->flags);
+  if (s->h_err) cudaFreeHost(s->h_err);
   delete s;
   t->shard = nullptr;
 }
@@ -1015,8 +1033,11 @@ int tc_shard_run(bvg_plan* p, int phase, const void* latent, int latent_dtype, c
   TcPlan* t = static_cast<TcPlan*>(p->tc);
   ShardState* s = shard_of(p);
   if (!s || !s->ready) return fail(BVG_ERR_STATE, "shard not set up");
-  if (p->ws[0] != s->exported_ws0)
+  if (p->ws[0] != s->exported_ws[0] || p->ws[1] != s->exported_ws[1])
     return fail(BVG_ERR_STATE, "workspace was re-allocated after bvg_shard_setup; set the shard up again");
+  if (*reinterpret_cast<volatile int*>(s->h_err))
+    return fail(BVG_ERR_STATE, "time-split decode: an earlier phase timed out waiting for the %s neighbour's halo",
+                *s->h_err == 1 ? "left" : "right");
   const int S = s->S, H = kShardMargin, Fs = s->Fs;
   BVG_REQUIRE(phase >= 0 && phase <= S, "phase %d outside [0,%d]", phase, S);
   const int own = s->g.f_end - s->g.f_begin;
@@ -1033,7 +1054,7 @@ int tc_shard_run(bvg_plan* p, int phase, const void* latent, int latent_dtype, c
       return rc;
   } else if (wait && (hasl || hasr)) {
     k_halo_wait<<<1, 1, 0, st>>>(hasl ? s->flags + phase : nullptr, hasr ? s->flags + 16 + phase : nullptr, epoch,
-                                 s->flags + 32);
+                                 s->d_err);
     BVG_CUDA(cudaGetLastError());
     ++p->last_launches;
   }
@@ -1089,11 +1110,11 @@ int tc_shard_run(bvg_plan* p, int phase, const void* latent, int latent_dtype, c
   return 0;
 }
 
-int tc_shard_error(bvg_plan* p) {
+int tc_shard_error(bvg_plan* p, int clear) {
   ShardState* s = shard_of(p);
   if (!s || !s->ready) return -1;
-  int e = 0;
-  if (cudaMemcpy(&e, s->flags + 32, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+  const int e = *reinterpret_cast<volatile int*>(s->h_err);   // mapped pinned word: no device access
+  if (clear) *s->h_err = 0;
   return e;
 }
 

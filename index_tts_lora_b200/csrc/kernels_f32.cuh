@@ -341,14 +341,13 @@ __global__ void __launch_bounds__(256) k_convtr_f32(const ConvTrArgs a) {
 // One thread -> 4 consecutive outputs; x window of 16, s window of 18, all in registers.
 // ---------------------------------------------------------------------------------------
 template <typename T_io>
-__global__ void __launch_bounds__(256) k_act1d(const T_io* __restrict__ x, T_io* __restrict__ y,
-                                               int C, int T, const ActParams ap) {
+__device__ __forceinline__ void act1d_body(const T_io* __restrict__ x, T_io* __restrict__ y, int C, int T,
+                                           const ActParams& ap, float a, float invb) {
   const int m0 = 4 * (blockIdx.x * 256 + threadIdx.x);
   if (m0 >= T) return;
   const int c = blockIdx.y, b = blockIdx.z;
   const T_io* xr = x + ((size_t)b * C + c) * T;
   T_io* yr = y + ((size_t)b * C + c) * T;
-  const float a = __ldg(ap.a + c), invb = __ldg(ap.invb + c);
   float xw[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
@@ -373,6 +372,26 @@ __global__ void __launch_bounds__(256) k_act1d(const T_io* __restrict__ x, T_io*
     else if constexpr (std::is_same<T_io, __nv_bfloat16>::value) yr[m0 + r] = __float2bfloat16_rn(z);
     else yr[m0 + r] = __float2half_rn(z);
   }
+}
+
+// The op boundary (bvg_activation1d): everything the reference op takes as a tensor stays a DEVICE pointer — the 12
+// taps of each filter, alpha and beta — so the call neither copies to the host nor synchronises; like the reference's
+// launch (anti_alias_activation_cuda.cu:209) it is one asynchronous kernel on the caller's stream and can be
+// captured into a CUDA graph.  a = exp(alpha), 1/(exp(beta)+1e-9) are evaluated per thread (activations.py:116-120).
+template <typename T_io>
+__global__ void __launch_bounds__(256) k_act1d(const T_io* __restrict__ x, T_io* __restrict__ y, int C, int T,
+                                               const float* __restrict__ up_filter,
+                                               const float* __restrict__ down_filter,
+                                               const float* __restrict__ alpha, const float* __restrict__ beta,
+                                               int logscale) {
+  ActParams ap;
+  ap.a = nullptr; ap.invb = nullptr;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) { ap.up[i] = __ldg(up_filter + i); ap.dn[i] = __ldg(down_filter + i); }
+  const float al = __ldg(alpha + blockIdx.y), be = __ldg(beta + blockIdx.y);
+  const float a = logscale ? expf(al) : al;
+  const float invb = 1.0f / ((logscale ? expf(be) : be) + 1e-9f);
+  act1d_body<T_io>(x, y, C, T, ap, a, invb);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -23,7 +23,8 @@ int tc_shard_export(bvg_plan* p, uint8_t* handles);
 int tc_shard_connect(bvg_plan* p, int side, const uint8_t* handles, void* ws0, void* ws1, void* flags);
 int tc_shard_run(bvg_plan* p, int phase, const void* latent, int latent_dtype, const float* spk_emb, void* wav_out,
                  int wav_dtype, int epoch, int wait, cudaStream_t st);
-int tc_shard_error(bvg_plan* p);
+int tc_shard_error(bvg_plan* p, int clear);
+bool tc_shard_pins_ws(const bvg_plan* p);
 // helpers implemented in bvg_api.cu (SIMT kernels reused by the tcgen05 path on the blocked layout)
 int tc_ensure_ws(bvg_plan* p, size_t bytes_per_buf);
 int simt_convtr_blk(bvg_plan* p, const void* x_blk, void* out_blk, int stage, int B, int Tmax, const int* d_len,

@@ -123,7 +123,13 @@ class TimeSplitP2P:
                 self.epoch, int(wait), _lib.stream_ptr(dev)), f"bvg_shard_run(phase {phase})")
 
     def decode(self, win: torch.Tensor, emb: torch.Tensor, out_dtype=torch.float32) -> torch.Tensor:
-        """All phases on this rank (multi-process use: neighbours run the same call concurrently)."""
+        """All phases on this rank (multi-process use: neighbours run the same call concurrently).
+
+        A phase that times out waiting for a neighbour's halo rows (~4 s) leaves a code in a mapped host word; the
+        waveform of that decode is then garbage.  The word is checked here for the PREVIOUS decode (free: no device
+        access) and every later phase of the plan refuses to run; call ``check()`` after synchronising the stream to
+        validate the decode just enqueued."""
+        self.check()
         self.epoch += 1
         out = torch.empty((self.fe - self.fb) * self.up, device=self.device, dtype=out_dtype)
         e = emb.reshape(1, -1).float().contiguous()
@@ -133,9 +139,11 @@ class TimeSplitP2P:
         return out
 
     def check(self):
+        """Raise if a phase enqueued so far timed out on a neighbour (final once the stream is synchronised)."""
         e = self.lib.bvg_shard_error(self.plan)
-        if e:
-            raise RuntimeError(f"time-split decode: timed out waiting for neighbour (code {e})")
+        if e > 0:
+            raise RuntimeError("time-split decode: timed out waiting for the "
+                               f"{'left' if e == 1 else 'right'} neighbour's halo rows; the waveform is invalid")
 
 
 def emulate_time_split(models: Sequence, latent_full: torch.Tensor, emb: torch.Tensor,
