@@ -236,7 +236,8 @@ int bvg_amp_layer(const float* x, float* y, const float* resid, int B, int C_in,
                   const float* beta, int logscale, int precision, void* stream);
 
 /* ConvTranspose1d(C_in, C_out, k, stride=u, padding=(k-u)/2) (models.py:157-163), fp32
- * [B,C_in,T] -> [B,C_out,T*u];  w [C_in, C_out, k]. */
+ * [B,C_in,T] -> [B,C_out,T*u];  w [C_in, C_out, k].  precision BVG_PREC_BF16 runs the decode's tcgen05 launch
+ * ((k/u)-tap implicit GEMM, operands rounded to bf16; channels must be multiples of 8). */
 int bvg_conv_transpose1d(const float* x, float* y, int B, int C_in, int C_out, int T,
                          const float* w, const float* bias, int k, int u, int precision,
                          void* stream);

@@ -109,6 +109,13 @@ __device__ __forceinline__ void umma_ts_f16(uint32_t tmem_d, uint32_t tmem_a, u6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
       ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+__device__ __forceinline__ void umma_ts_f16_e(uint32_t leader, uint32_t tmem_d, uint32_t tmem_a, u64 bdesc, uint32_t idesc,
+                                              uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 e, %5, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc), "r"(leader) : "memory");
+}
 __device__ __forceinline__ uint32_t f2_to_h2_sat(float lo, float hi) {     // {hi, lo} -> packed fp16x2, finite-saturating
   uint32_t r;
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -415,7 +422,9 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
       }
     } else if (warp == WARP_UP) {
       // ===================== up-FIR MMA issuer: D1[half] = X(blocks of the half) * (UP_hi + UP_lo) =====================
-      if (lane == 0) {
+      // (warp-convergent: every lane walks the loop, the elected lane issues — see umma_bf16_e in amp_tc.cuh)
+      {
+        const uint32_t leader = elect_one();
         // A = x tile, MN-major SWIZZLE_NONE (LBO = stride between 8-row K groups, SBO = stride between 8-channel M groups)
         const uint32_t idesc_up = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(16 >> 3) << 17) |
                                   ((uint32_t)(128 >> 4) << 24);
@@ -434,17 +443,18 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
             for (int i = 0; i < nb; ++i) {
               if (BVG_DBGBIT(a, 256) && i > 0) break;          // timing experiments only
               const uint32_t td = tmem + TM_D1 + (uint32_t)(h * 96 + i * 16);
-              umma_bf16(td, hiA | (a0 + (b0 + i) * 8), bhi, idesc_up, 0u);
-              umma_bf16(td, hiA | (a0 + (b0 + i) * 8), blo, idesc_up, 1u);
+              umma_bf16_e(leader, td, hiA | (a0 + (b0 + i) * 8), bhi, idesc_up, 0u);
+              umma_bf16_e(leader, td, hiA | (a0 + (b0 + i) * 8), blo, idesc_up, 1u);
             }
-            umma_commit(BAR_DFULL(h));
+            umma_commit_e(leader, BAR_DFULL(h));
           }
-          umma_commit(BAR_XEMPTY(xs));
+          umma_commit_e(leader, BAR_XEMPTY(xs));
         }
       }
     } else if (warp == WARP_DN) {
       // ===================== down-FIR MMA issuer: D2[half] = S(z-block windows, TMEM) * DN =====================
-      if (lane == 0) {
+      {
+        const uint32_t leader = elect_one();
         const uint32_t idesc_dn = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // fp16 x fp16
         const u64 bdn = make_sdesc(s_base + FOFF_DNB, 16 * 16, 128);
         for (int n = 0; n < total_chunks; ++n) {
@@ -460,16 +470,17 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
               const int r0 = (16 * (z0 + i) < S - 16) ? 16 * (z0 + i) : S - 16;
 #pragma unroll
               for (int ks = 0; ks < 3; ++ks)
-                umma_ts_f16(tmem + TM_D2 + (uint32_t)(h * 48 + i * 16), tmem + TM_S + (uint32_t)(r0 + ks * 8), bdn + (u64)(ks * 32),
-                            idesc_dn, ks > 0);
+                umma_ts_f16_e(leader, tmem + TM_D2 + (uint32_t)(h * 48 + i * 16), tmem + TM_S + (uint32_t)(r0 + ks * 8),
+                              bdn + (u64)(ks * 32), idesc_dn, ks > 0);
             }
-            umma_commit(BAR_D2FULL(h));
+            umma_commit_e(leader, BAR_D2FULL(h));
           }
         }
       }
     } else if (warp == WARP_CONV) {
       // ===================== conv MMA issuer (as k_amp_tc, A = z ring) =====================
-      if (lane == 0) {
+      {
+        const uint32_t leader = elect_one();
         const uint32_t idesc = make_idesc_bf16(128, n_tile);
         const uint32_t lboA = ZRF * 16, lboB = (uint32_t)n_tile * 16;
         const u64 hiA = make_sdesc(0, lboA, 128), hiB = make_sdesc(0, lboB, 128);
@@ -496,18 +507,18 @@ k_amp_fir(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ TcArg
                 const uint32_t a0 = aU + (uint32_t)((s * tps + tj) * a.dil);
                 const uint32_t b0 = wU + (uint32_t)tj * tileU;
                 if (BVG_DBGBIT(a, 4)) continue;                 // timing experiments only
-                umma_bf16(tm, hiA | a0, hiB | b0, idesc, accflag);
-                umma_bf16(tm, hiA | (a0 + ksA), hiB | (b0 + ksB), idesc, 1u);
-                umma_bf16(tm + n_tile, hiA | (a0 + 128), hiB | b0, idesc, accflag);
-                umma_bf16(tm + n_tile, hiA | (a0 + 128 + ksA), hiB | (b0 + ksB), idesc, 1u);
+                umma_bf16_e(leader, tm, hiA | a0, hiB | b0, idesc, accflag);
+                umma_bf16_e(leader, tm, hiA | (a0 + ksA), hiB | (b0 + ksB), idesc, 1u);
+                umma_bf16_e(leader, tm + n_tile, hiA | (a0 + 128), hiB | b0, idesc, accflag);
+                umma_bf16_e(leader, tm + n_tile, hiA | (a0 + 128 + ksA), hiB | (b0 + ksB), idesc, 1u);
                 accflag = 1u;
               }
-              umma_commit(BAR_WEMPTY(stage));
+              umma_commit_e(leader, BAR_WEMPTY(stage));
               if (++stage == W_STAGES_F) { stage = 0; phase ^= 1; }
             }
-            umma_commit(BAR_ZEMPTY(zs));
+            umma_commit_e(leader, BAR_ZEMPTY(zs));
           }
-          umma_commit(BAR_ACCFULL(as));
+          umma_commit_e(leader, BAR_ACCFULL(as));
         }
       }
     }

@@ -414,6 +414,10 @@ void tc_pack_conv_w(const float* w, float* wp, int Cout, int Cin, int K, cudaStr
   const size_t n = (size_t)Cout * Cin * K;
   k_pack_conv_w<<<(int)std::min<size_t>((n + 255) / 256, 4096), 256, 0, st>>>(w, wp, Cout, Cin, K);
 }
+void tc_pack_convtr_w(const float* w, float* wp, int Cin, int Cout, int K, cudaStream_t st) {
+  const size_t n = (size_t)Cout * Cin * K;
+  k_pack_convtr_w<<<(int)std::min<size_t>((n + 255) / 256, 4096), 256, 0, st>>>(w, wp, Cin, Cout, K);
+}
 void tc_snake_params(const float* alpha, const float* beta, float* a, float* invb, int C, int logscale,
                      cudaStream_t st) {
   k_snake_params<<<ceil_div(C, 128), 128, 0, st>>>(alpha, beta, a, invb, C, logscale);
@@ -838,8 +842,8 @@ int bvg_conv_transpose1d(const float* x, float* y, int B, int C_in, int C_out, i
   BVG_CUDA(cudaGetDevice(&dev));
   if ((rc = check_device(dev, nullptr))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (precision != BVG_PREC_F32)
-    return fail(BVG_ERR_UNSUPPORTED, "bvg_conv_transpose1d: only the fp32 per-op path is exposed");
+  if (precision == BVG_PREC_BF16) return tc_conv_transpose(x, y, B, C_in, C_out, T, w, bias, k, u, st);
+  BVG_REQUIRE(precision == BVG_PREC_F32, "bvg_conv_transpose1d: unknown precision");
   AsyncTmp tmp(st);
   float* wp;
   const size_t n = (size_t)C_out * C_in * k;

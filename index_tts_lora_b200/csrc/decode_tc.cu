@@ -920,6 +920,11 @@ int tc_shard_setup(bvg_plan* p, const bvg_shard_geom* g, cudaStream_t st) {
   s->ready = false;                      // a new geometry may grow the workspace (and must then be re-exported)
   const int S = p->n_stages, own = g->f_end - g->f_begin;
   BVG_REQUIRE(g->f_begin >= 0 && own > 0 && g->f_end <= g->f_total, "bad shard range");
+  // Back-to-back decodes need no host barrier between them: a rank can only finish decode n after its neighbours
+  // have sent it their last halo of decode n, i.e. after every neighbour kernel that reads the stage buffer of the
+  // OTHER parity has run; the first peer store of decode n+1 (end of phase 0) lands in stage buffer 1 while a lagging
+  // neighbour is at most in its final phase S, which reads buffer S & 1 — disjoint for even S.
+  BVG_REQUIRE(S % 2 == 0, "the time split needs an even number of upsampling stages (%d)", S);
   BVG_REQUIRE(g->own_max >= own, "own_max smaller than this shard");
   // receptive field of one stage at its output rate: deepest AMP block
   int kmax = 0, rows_out = 0;
@@ -1177,6 +1182,57 @@ int tc_amp_layer(const float* x, float* y, const float* resid, int B, int C_in, 
     k_blk_to_cm<<<g3, 128, 0, st>>>(yb, y, C_out, T);
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) rc = fail(BVG_ERR_CUDA, "tc_amp_layer: %s", cudaGetErrorString(e));
+  }
+  cleanup();
+  return rc;
+}
+
+// ConvTranspose1d(C_in, C_out, k, stride u, padding (k-u)/2) through the SAME tcgen05 launch as the decode
+// (models.py:157-163,232-233): (k/u)-tap implicit GEMM over the input rate, phase-scatter epilogue.  fp32 [B,C,T] in/out,
+// operands rounded to bf16.  Test entry point: packs per call and synchronises.
+int tc_conv_transpose(const float* x, float* y, int B, int C_in, int C_out, int T, const float* w, const float* bias,
+                      int k, int u, cudaStream_t st) {
+  BVG_REQUIRE(C_in % 8 == 0 && C_out % 8 == 0, "tcgen05 per-op path: channels must be multiples of 8");
+  BVG_REQUIRE(k / u - 1 <= X_LEAD, "tcgen05 ConvTranspose1d: at most %d taps per phase", X_LEAD + 1);
+  std::vector<void*> tmp;
+  auto cleanup = [&]() { for (void* q : tmp) cudaFree(q); };
+  auto alloc = [&](void** ptr, size_t bytes) { cudaError_t e = cudaMalloc(ptr, bytes); if (e == cudaSuccess) tmp.push_back(*ptr); return e; };
+  ConvW cw;
+  cw.Cin = C_in; cw.Cout = C_out; cw.K = k;
+  const size_t nw = (size_t)C_out * C_in * k;
+  __nv_bfloat16 *xb, *yb;
+  if (alloc((void**)&cw.wp, nw * 4) || alloc((void**)&xb, (size_t)B * C_in * T * 2) ||
+      alloc((void**)&yb, (size_t)B * C_out * T * u * 2)) {
+    cleanup();
+    return fail(BVG_ERR_CUDA, "tc_conv_transpose: allocation failed");
+  }
+  tc_pack_convtr_w(w, cw.wp, C_in, C_out, k, st);
+  TcLayer L;
+  std::vector<void*> owned;
+  int rc = build_layer_tr(owned, L, cw, u, st);
+  for (void* q : owned) tmp.push_back(q);
+  if (rc) { cleanup(); return rc; }
+  dim3 g(ceil_div(T, 128), C_in / 8, B);
+  k_cm_to_blk<<<g, 128, 0, st>>>(x, xb, C_in, T);
+  CUtensorMap map;
+  if ((rc = make_map(xb, C_in, T, B, &map))) { cleanup(); return rc; }
+  ConvW cg = cw;                       // the GEMM's view: u*C_out phase-major columns, k/u taps
+  cg.Cout = u * C_out; cg.K = k / u; cg.bias = const_cast<float*>(bias);
+  TcLaunch q;
+  q.x = xb; q.out = yb; q.dil = 1; q.B = B; q.Tstride = T; q.out_tstride = T * u; q.rate = 1; q.d_len = nullptr;
+  q.up = u; q.pad = (k - u) / 2; q.cphase = C_out; q.cls = 2;
+  {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    q.sm_count = sms;
+  }
+  rc = launch_tc(nullptr, map, L, cg, nullptr, q, st);
+  if (!rc) {
+    dim3 g3(ceil_div(T * u, 128), C_out / 8, B);
+    k_blk_to_cm<<<g3, 128, 0, st>>>(yb, y, C_out, T * u);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = fail(BVG_ERR_CUDA, "tc_conv_transpose: %s", cudaGetErrorString(e));
   }
   cleanup();
   return rc;

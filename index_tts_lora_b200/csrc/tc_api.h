@@ -12,6 +12,9 @@ int tc_amp_layer(const float* x, float* y, const float* resid, int B, int C_in, 
                  const float* w, const float* bias, int k, int dilation, int act,
                  const float* up_filter, const float* down_filter, const float* alpha,
                  const float* beta, int logscale, cudaStream_t st);
+int tc_conv_transpose(const float* x, float* y, int B, int C_in, int C_out, int T, const float* w, const float* bias,
+                      int k, int u, cudaStream_t st);
+void tc_pack_convtr_w(const float* w, float* wp, int Cin, int Cout, int K, cudaStream_t st);
 int tc_set_fir_max_c(int v);
 int tc_set_split_min_c(int v);
 int tc_set_residual_mma(int on);

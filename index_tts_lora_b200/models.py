@@ -216,7 +216,11 @@ class BigVGAN(nn.Module):
         self._plan_device: Optional[torch.device] = None
         self._weights_dirty = True
         self.precision: Optional[str] = None       # None = follow parameter dtype
-        self.cache_speaker_embedding = False
+        # the caller keeps ONE prompt mel for all sentences of a request (infer.py:605-617,789-800)
+        # but models.py:204 re-runs the speaker encoder on it every call.  The embedding is cached by the identity of
+        # the mel tensor (storage, offset, shape, strides, dtype AND its in-place version counter; the storage is kept
+        # alive so the address cannot be recycled): exact, and free for every sentence after the first.
+        self.cache_speaker_embedding = True
         self._spk_cache = None
         # The ECAPA encoder is ~60 tiny kernels: launch-bound (2.9 ms eager on a B200 for a
         # [1,300,100] prompt, against a 3.2 ms generator decode).  In eval mode on CUDA it is
@@ -353,6 +357,16 @@ class BigVGAN(nn.Module):
         if pdt != torch.float32 and mel_ref.is_cuda and not torch.is_autocast_enabled():
             with torch.autocast("cuda", dtype=pdt):
                 return self.speaker_encoder(mel_ref, lens)
+        if pdt == torch.float32 and mel_ref.is_cuda and not torch.is_autocast_enabled():
+            # the fp32 exactness path must not consume a TF32 embedding: cuDNN convolutions default to
+            # allow_tf32=True (SURVEY §8c asks for TF32 off on every same-device cross-check)
+            mm = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = False
+            try:
+                with torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=False, allow_tf32=False):
+                    return self.speaker_encoder(mel_ref, lens)
+            finally:
+                torch.backends.cuda.matmul.allow_tf32 = mm
         return self.speaker_encoder(mel_ref, lens)
 
     def _speaker_encoder_graphed(self, mel_ref):
