@@ -199,6 +199,13 @@ int bvg_plan_read_profile(bvg_plan* plan, bvg_profile* out);
  * Returns the previous value. */
 int bvg_set_tc_fir_max_channels(int max_c);
 
+/* bf16 path: square activated AMP layers with C <= max_c channels (at most 96) take k_amp_nar (csrc/amp_nar.cuh): both
+ * kaiser-sinc FIRs of Activation1d as banded-Toeplitz tcgen05 MMAs streamed block by block through TMEM rings, SnakeBeta
+ * on the CUDA cores, the dilated conv as in k_amp_tc.  Experimental (slower than k_amp_tc as measured).
+ * Process-wide.  Default 0 = every layer on k_amp_tc (or the BVG_NAR_MAX_C environment variable at first use); 96 = all
+ * three narrow stages.  Returns the previous value. */
+int bvg_set_tc_narrow_max_channels(int max_c);
+
 /* bf16 path: AMP layers with C_in >= min_c run in split form — Activation1d once per layer in a streaming kernel
  * (csrc/act_blk.cuh) into an L2-sized scratch buffer, then the dilated conv as the same tcgen05 kernel without its
  * activation role — instead of the fused kernel, which repeats the activation for every 256-wide column tile of the

@@ -8,7 +8,7 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbvg.so")
+LIB_PATH = os.environ.get("BVG_LIB") or os.path.join(_HERE, "libbvg.so")   # BVG_LIB: experiment builds (tools/)
 
 BVG_F32, BVG_BF16, BVG_F16, BVG_I16 = 0, 1, 2, 3
 PREC_F32, PREC_BF16 = 0, 1
@@ -81,6 +81,7 @@ SYMBOLS = {
     "bvg_plan_set_profiling": (_I, [_P, _I]),
     "bvg_plan_read_profile": (_I, [_P, C.POINTER(BvgProfile)]),
     "bvg_set_tc_fir_max_channels": (_I, [_I]),
+    "bvg_set_tc_narrow_max_channels": (_I, [_I]),
     "bvg_set_tc_split_min_channels": (_I, [_I]),
     "bvg_set_tc_residual_mma": (_I, [_I]),
     "bvg_activation1d": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P]),

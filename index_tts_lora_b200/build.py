@@ -8,7 +8,10 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libbvg.so")
+# BVG_EXPERIMENTS=1 builds libbvg_exp.so with the timing knock-outs / pipeline trace compiled in (tools/ only; the
+# shipped library never contains them); _lib.py loads it when BVG_LIB points at it
+EXPERIMENTS = os.environ.get("BVG_EXPERIMENTS") == "1"
+OUT = os.path.join(HERE, "libbvg_exp.so" if EXPERIMENTS else "libbvg.so")
 SOURCES = ["bvg_api.cu", "decode_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
@@ -33,7 +36,7 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return OUT
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-DBVG_EXPERIMENTS"] if EXPERIMENTS else []) + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = os.path.join(HERE, "build.log")
     with open(log, "w") as f:

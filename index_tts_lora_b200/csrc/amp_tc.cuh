@@ -99,6 +99,7 @@ struct TcArgs {
   int up, pad, cphase;
   const float* a2;             // [Cin padded to 32]  2*exp(alpha)
   const float* nhb;            // [Cin padded to 32]  -0.5/(exp(beta)+1e-9)
+  long long* trace;            // BVG_EXPERIMENTS builds only: clock-stamped pipeline events of CTA 0 (tools/nar_trace.py)
   float up2[12];               // 2*f[k]  (the x2 gain of resample.py:30 folded in)
   float dn[12];
 };

@@ -229,7 +229,13 @@ static int ensure_ws(bvg_plan* p, size_t bytes_per_buf) {
     p->ws[i] = nullptr;
   }
   p->ws_bytes = 0;
-  for (int i = 0; i < 4; ++i) BVG_CUDA(cudaMalloc(&p->ws[i], bytes_per_buf));
+  // Zero-filled once: rows past an utterance's end are only ever written where a consumer's zero padding needs them,
+  // and the banded-Toeplitz FIR MMAs (amp_nar.cuh) multiply stale rows by zero taps — which must not be NaN / Inf bit
+  // patterns of uninitialised memory.  Everything the kernels write afterwards is finite.
+  for (int i = 0; i < 4; ++i) {
+    BVG_CUDA(cudaMalloc(&p->ws[i], bytes_per_buf));
+    BVG_CUDA(cudaMemset(p->ws[i], 0, bytes_per_buf));
+  }
   p->ws_bytes = bytes_per_buf;
   return 0;
 }
@@ -721,6 +727,7 @@ int bvg_plan_set_profiling(bvg_plan* p, int enable) {
 }
 
 int bvg_set_tc_fir_max_channels(int max_c) { return bvg::tc_set_fir_max_c(max_c); }
+int bvg_set_tc_narrow_max_channels(int max_c) { return bvg::tc_set_nar_max_c(max_c); }
 int bvg_set_tc_split_min_channels(int min_c) { return bvg::tc_set_split_min_c(min_c); }
 int bvg_set_tc_residual_mma(int on) { return bvg::tc_set_residual_mma(on); }
 

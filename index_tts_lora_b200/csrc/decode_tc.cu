@@ -13,6 +13,7 @@
 
 #include "act_blk.cuh"
 #include "amp_fir.cuh"
+#include "amp_nar.cuh"
 #include "amp_tc.cuh"
 #include "tc_api.h"
 
@@ -376,6 +377,19 @@ static int get_map(TcPlan* t, const void* base, int C, int Tstride, int B, CUten
   return 0;
 }
 
+#ifdef BVG_EXPERIMENTS
+static long long* g_trace = nullptr;
+extern "C" int bvg_exp_dump_trace(void) {
+  if (!g_trace) return -1;
+  std::vector<long long> h(8192);
+  cudaDeviceSynchronize();
+  cudaMemcpy(h.data(), g_trace, 4096 * 16, cudaMemcpyDeviceToHost);
+  for (int i = 0; i < 4096; ++i)
+    if (h[2 * i]) fprintf(stderr, "nar_trace %d %lld %lld\n", i, h[2 * i], h[2 * i + 1]);
+  return 0;
+}
+#endif
+
 // ------------------------------------------------------------------------------ launch
 struct TcLaunch {
   const void* x;                // blocked bf16 input
@@ -436,6 +450,35 @@ static int launch_fir_inst(const CUtensorMap& map, const TcArgs& a, dim3 grid, c
   kern<<<grid, fir::NTHREADS_F, fir::F_SMEM, st>>>(map, a);
   BVG_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <int NUB, bool RM>
+static int launch_nar_inst(const CUtensorMap& map, const CUtensorMap& mapr, const CUtensorMap& mapq, const TcArgs& a, dim3 grid,
+                           cudaStream_t st) {
+  auto kern = nar::k_amp_nar<NUB, RM>;
+  BVG_CUDA(func_attr_once((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, nar::N_SMEM));
+  kern<<<grid, nar::NTHREADS_N, nar::N_SMEM, st>>>(map, mapr, mapq, a);
+  BVG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Square activated layers with C <= this many channels take k_amp_nar (amp_nar.cuh: both FIRs of Activation1d streamed
+// through the tensor cores); 0 = every layer on k_amp_tc.  Default 0: parity-green (50 dB per layer, like k_amp_tc) but
+// measured 19.9 ms against 13.2 ms for the narrow stages of a 16 x 10 s decode (the single-thread MMA
+// issuers and the per-block hand-overs are latency bound, and halo / idle-lane waste eats the instruction savings).
+constexpr int kNarMaxCDefault = 0;
+static std::atomic<int> g_nar_max_c{-1};
+int tc_set_nar_max_c(int v) {
+  const int cur = g_nar_max_c.load(), old = cur < 0 ? kNarMaxCDefault : cur;
+  g_nar_max_c = v < 0 ? 0 : v;
+  return old;
+}
+static int nar_max_c() {
+  if (g_nar_max_c < 0) {
+    const char* e = getenv("BVG_NAR_MAX_C");
+    g_nar_max_c = e ? atoi(e) : kNarMaxCDefault;
+  }
+  return g_nar_max_c;
 }
 
 // narrow activated layers may take k_amp_fir (both FIRs on the tensor cores): opt-in, see bvg_set_tc_fir_max_channels
@@ -557,6 +600,19 @@ static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, cons
   {
     static const int dbg = [] { const char* e = getenv("BVG_DBG"); return e ? atoi(e) : 0; }();
     a.dbg = dbg;
+    // BVG_TRACE_LAYER=<cls>,<C>,<K>,<dil>: the matching k_amp_nar launches stamp their pipeline events into a device buffer
+    // that is dumped to stderr by bvg_exp_dump_trace()
+    static const std::tuple<int, int, int> tl = [] {
+      int c = 0, k = 0, d = 0;
+      const char* e = getenv("BVG_TRACE_LAYER");
+      if (!e || sscanf(e, "%d,%d,%d", &c, &k, &d) != 3) return std::make_tuple(0, 0, 0);
+      return std::make_tuple(c, k, d);
+    }();
+    if (std::get<0>(tl) == cw.Cin && std::get<1>(tl) == cw.K && std::get<2>(tl) == q.dil && aw) {
+      if (!g_trace) { cudaMalloc(&g_trace, 4096 * 16); }
+      cudaMemsetAsync(g_trace, 0, 4096 * 16, st);
+      a.trace = g_trace;
+    }
   }
 #endif
   const int hc = q.dil * (cw.K - 1) / 2;
@@ -582,7 +638,38 @@ static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, cons
   int rc;
   const bool use_fir = aw && !q.up && L.n_tiles == 1 && L.n_tile <= fir::MAX_NTILE_F && cw.Cin <= fir_max_c() &&
                        cw.Cout <= fir_max_c() && hc <= 32;
-  if (use_fir) {
+  const bool use_nar = !use_fir && aw && !q.up && L.n_tiles == 1 && L.n_tile <= nar::MAX_NTILE_N && cw.Cin == cw.Cout &&
+                       cw.Cin <= nar_max_c() && hc <= 32;
+  if (use_nar) {
+    // x tile = 16 TMA boxes {8 channels, 96 rows} (4 time segments x 4 channel groups); residual / running sum as D += R x I
+    TcPlan* t = p ? static_cast<TcPlan*>(p->tc) : nullptr;
+    CUtensorMap xm, tmpr, tmpq;
+    rc = t ? get_map(t, q.x, cw.Cin, q.Tstride, q.B, &xm, 0, fir::XB) : make_map(q.x, cw.Cin, q.Tstride, q.B, &xm, 0, fir::XB);
+    if (rc) return rc;
+    const CUtensorMap* mr = &xm;
+    const CUtensorMap* mq = &xm;
+    a.xin = static_cast<const __nv_bfloat16*>(q.x);
+    a.xgroups = cw.Cin / 8;
+    const bool rm = residual_mma_on() && L.idw && (q.resid || q.acc_in);
+    if (rm) {
+      if (q.resid) {
+        mr = &tmpr;
+        rc = t ? get_map(t, q.resid, cw.Cout, a.Tstride, q.B, &tmpr, 0, 128) : make_map(q.resid, cw.Cout, a.Tstride, q.B, &tmpr, 0, 128);
+      }
+      if (!rc && q.acc_in) {
+        mq = &tmpq;
+        rc = t ? get_map(t, q.acc_in, cw.Cout, a.Tstride, q.B, &tmpq, q.acc_rows, 128)
+               : make_map(q.acc_in, cw.Cout, a.Tstride, q.B, &tmpq, q.acc_rows, 128);
+      }
+      if (rc) return rc;
+      a.idw = L.idw; a.nchr = (L.n_tile + 31) / 32;
+      a.rmma_r = q.resid ? 1 : 0; a.rmma_q = q.acc_in ? 1 : 0;
+      a.resid = nullptr; a.acc_in = nullptr;       // the epilogue warps see a plain conv
+    }
+    const bool plain = !(a.resid || a.acc_in);      // RM instantiation = plain-only epilogue
+    if (hc <= 16) rc = plain ? launch_nar_inst<10, true>(xm, *mr, *mq, a, grid, st) : launch_nar_inst<10, false>(xm, *mr, *mq, a, grid, st);
+    else rc = plain ? launch_nar_inst<11, true>(xm, *mr, *mq, a, grid, st) : launch_nar_inst<11, false>(xm, *mr, *mq, a, grid, st);
+  } else if (use_fir) {
     // x tile = 16 TMA boxes {8 channels, 96 rows} (4 time segments x 4 channel groups)
     CUtensorMap fm;
     TcPlan* t = p ? static_cast<TcPlan*>(p->tc) : nullptr;
@@ -664,6 +751,7 @@ static int tc_prepare(bvg_plan* p, TcPlan* t, int B, int Fs) {
     if (t->lat_blk) BVG_CUDA(cudaFree(t->lat_blk));
     t->lat_blk = nullptr; t->lat_bytes = 0;
     BVG_CUDA(cudaMalloc(&t->lat_blk, lat_need));
+    BVG_CUDA(cudaMemset(t->lat_blk, 0, lat_need));
     t->lat_bytes = lat_need;
     t->maps.clear();
   }
@@ -671,7 +759,10 @@ static int tc_prepare(bvg_plan* p, TcPlan* t, int B, int Fs) {
     BVG_CUDA(cudaDeviceSynchronize());
     for (void*& qb : t->cbuf) { if (qb) BVG_CUDA(cudaFree(qb)); qb = nullptr; }
     t->cbuf_bytes = 0;
-    for (void*& qb : t->cbuf) BVG_CUDA(cudaMalloc(&qb, buf_bytes));
+    for (void*& qb : t->cbuf) {
+      BVG_CUDA(cudaMalloc(&qb, buf_bytes));
+      BVG_CUDA(cudaMemset(qb, 0, buf_bytes));       // see ensure_ws: stale rows must be finite
+    }
     t->cbuf_bytes = buf_bytes;
     t->maps.clear();
   }
@@ -684,7 +775,10 @@ static int tc_prepare(bvg_plan* p, TcPlan* t, int B, int Fs) {
     BVG_CUDA(cudaDeviceSynchronize());
     for (void*& qb : t->zbuf) { if (qb) BVG_CUDA(cudaFree(qb)); qb = nullptr; }
     t->zbuf_bytes = 0;
-    for (void*& qb : t->zbuf) BVG_CUDA(cudaMalloc(&qb, z_bytes));
+    for (void*& qb : t->zbuf) {
+      BVG_CUDA(cudaMalloc(&qb, z_bytes));
+      BVG_CUDA(cudaMemset(qb, 0, z_bytes));
+    }
     t->zbuf_bytes = z_bytes;
     t->maps.clear();
   }
@@ -1146,6 +1240,7 @@ int tc_amp_layer(const float* x, float* y, const float* resid, int B, int C_in, 
     return fail(BVG_ERR_CUDA, "tc_amp_layer: allocation failed");
   }
   cw.bias = const_cast<float*>(bias);
+  cudaMemsetAsync(yb, 0, (size_t)B * C_out * T * 2, st);
   tc_pack_conv_w(w, cw.wp, C_out, C_in, k, st);
   if (act) {
     tc_snake_params(alpha, beta, a_dev, invb_dev, C_in, logscale, st);

@@ -16,6 +16,7 @@ int tc_conv_transpose(const float* x, float* y, int B, int C_in, int C_out, int 
                       int k, int u, cudaStream_t st);
 void tc_pack_convtr_w(const float* w, float* wp, int Cin, int Cout, int K, cudaStream_t st);
 int tc_set_fir_max_c(int v);
+int tc_set_nar_max_c(int v);
 int tc_set_split_min_c(int v);
 int tc_set_residual_mma(int on);
 // time-split P2P decode (decode_tc.cu)

@@ -419,6 +419,72 @@ def test_full_generator_bf16_tensor_core_fir_snr():
     assert snr > BF16_SNR_DB, snr
 
 
+# ============================================================================= streamed tensor-core FIR (amp_nar.cuh)
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,d", [(3, 1), (7, 3), (11, 5)])
+@pytest.mark.parametrize("C,T", [(24, 700), (48, 1500), (64, 129), (96, 600), (96, 5), (24, 3)])
+def test_amp_layer_bf16_streamed_fir_vs_oracle(k, d, C, T):
+    """Experimental k_amp_nar (both FIRs as tcgen05 MMAs streamed through TMEM block slots, csrc/amp_nar.cuh): several
+    chunks per tile (C = 64, 96), several tiles per CTA-less grid, edge tiles next to interior ones (the case that
+    exposed the mbarrier phase-aliasing race of slots shared between groups), T = 3 / 5."""
+    from index_tts_lora_b200.models import AMPBlock1
+    from index_tts_lora_b200.ops import amp_layer
+    from index_tts_lora_b200 import synth, _lib
+    from index_tts_lora_b200.config import AttrDict
+    O = _oracle()
+    dev = _dev()
+    lib = _lib.load()
+    blk = AMPBlock1(AttrDict(snake_logscale=True), C, k, (d, d, d), activation="snakebeta")
+    sd = synth.synth_state_dict(blk.state_dict(), seed=k * 100 + d, profile="stress")
+    blk.load_state_dict(sd)
+    x = torch.randn(2, C, T, generator=synth._gen(1, f"x{C}{T}"))
+    r = torch.randn(2, C, T, generator=synth._gen(2, f"r{C}{T}"))
+    ref = O.amp_layer(x, sd, "activations.0", "convs1.0", k, d) + r
+    old = lib.bvg_set_tc_narrow_max_channels(96)
+    try:
+        y = amp_layer(x.to(dev), blk.convs1[0], blk.activations[0], resid=r.to(dev), precision="bf16").cpu()
+    finally:
+        lib.bvg_set_tc_narrow_max_channels(old)
+    y0 = amp_layer(x.to(dev), blk.convs1[0], blk.activations[0], resid=r.to(dev), precision="bf16").cpu()
+    snr = _snr(ref, y)
+    assert snr > 35.0, snr
+    assert _snr(y0, y) > 40.0, _snr(y0, y)
+
+
+@pytest.mark.gpu
+def test_ragged_generator_bf16_streamed_fir_snr():
+    """Ragged real-config batch with k_amp_nar on all three narrow stages: every utterance >= 40 dB against the default
+    path's own output would hide a common error, so the reference is the fp32 path (itself < 1e-4 from the oracle)."""
+    from index_tts_lora_b200 import synth, _lib
+    from index_tts_lora_b200.config import default_config
+    from index_tts_lora_b200.models import BigVGAN
+    dev = _dev()
+    lib = _lib.load()
+    h = default_config()
+    m = BigVGAN(h)
+    m.load_state_dict(synth.synth_state_dict(m.state_dict(), seed=1234, profile="init"))
+    m = m.to(dev)
+    m.remove_weight_norm()
+    m.eval()
+    lengths = [61, 40, 17, 1]
+    lat = synth.synth_latent(len(lengths), max(lengths), h.gpt_dim, seed=9)
+    emb = m.speaker_embedding(synth.synth_mel(1, 300, h.num_mels, seed=1).to(dev))
+    m.precision = "fp32"
+    ref = m.decode(lat.to(dev), emb, lengths=lengths).cpu()
+    m.precision = "bf16"
+    old = lib.bvg_set_tc_narrow_max_channels(96)
+    try:
+        wav = m.decode(lat.to(dev).to(torch.bfloat16), emb, lengths=lengths, out_dtype=torch.float32).cpu()
+    finally:
+        lib.bvg_set_tc_narrow_max_channels(old)
+    for b, L in enumerate(lengths):
+        snr = _snr(ref[b, :, : L * 1024], wav[b, :, : L * 1024])
+        print("streamed FIR, utterance", b, L, "frames: SNR", snr)
+        assert snr > BF16_SNR_DB, (b, L, snr)
+        if L < max(lengths):
+            assert wav[b, :, L * 1024:].abs().max().item() == 0.0
+
+
 # ============================================================================= split form (act_blk.cuh)
 @pytest.mark.gpu
 @pytest.mark.parametrize("k,d", [(3, 1), (7, 3), (11, 5)])
