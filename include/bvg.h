@@ -221,6 +221,18 @@ int bvg_set_tc_split_min_channels(int min_c);
  * the order of the additions differs.  Process-wide; default on (or BVG_RMMA=0 at first use).  Returns the previous value. */
 int bvg_set_tc_residual_mma(int on);
 
+/* bf16 path, launch latency.  (1) Programmatic dependent launch: every kernel of a decode is launched with the
+ * programmatic-stream-serialization attribute, releases its successor first thing (griddepcontrol.launch_dependents)
+ * and waits for its predecessor (griddepcontrol.wait) only after its own prologue (TMEM allocation, mbarrier init, tile
+ * prefix table), so the prologue and the grid-launch latency of kernel n+1 overlap kernel n wherever SMs are free.
+ * (2) CUDA graphs: the part of a decode that only touches plan-owned buffers (conv_pre ... activation_post, 114 of the
+ * 118 launches on three streams) is stream-captured the second time a (B, Tmax, lengths) shape is seen and replayed
+ * afterwards; the launches that touch caller pointers stay ordinary launches, so latent / waveform addresses may change
+ * from call to call.  Results are bit-identical either way.  Process-wide, default on (BVG_PDL=0 / BVG_GRAPHS=0 at
+ * first use turn them off).  Both return the previous value. */
+int bvg_set_pdl(int on);
+int bvg_set_graphs(int on);
+
 /* ---- per-op entry points (tests, and the reference's own native-op boundary) ---------- */
 
 /* Supersedes anti_alias_activation_cuda.forward(input, up_filter, down_filter, alpha, beta)

@@ -84,6 +84,8 @@ SYMBOLS = {
     "bvg_set_tc_narrow_max_channels": (_I, [_I]),
     "bvg_set_tc_split_min_channels": (_I, [_I]),
     "bvg_set_tc_residual_mma": (_I, [_I]),
+    "bvg_set_pdl": (_I, [_I]),
+    "bvg_set_graphs": (_I, [_I]),
     "bvg_activation1d": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P]),
     "bvg_amp_layer": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P]),
     "bvg_conv_transpose1d": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _P]),

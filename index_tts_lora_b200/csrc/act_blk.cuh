@@ -46,6 +46,8 @@ __device__ __forceinline__ int ab_zero_bound(int T, int Tstride) {
 
 __global__ void __launch_bounds__(AB_WARPS * 32, 2) k_act_blk(const __grid_constant__ AbArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, p = lane & 3;
   uint8_t* my = smem + warp * AB_SMEM_PER_WARP;

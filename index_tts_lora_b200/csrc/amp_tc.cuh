@@ -125,20 +125,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
       "@P1 bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}\n" ::"r"(bar), "r"(parity) : "memory");
 }
-// Polite wait for the roles that are normally far ahead of the activation warps (producers,
-// epilogue): poll, then sleep `ns` so the polling does not eat the activation warps' issue slots.
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t ns) {
-  // try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or the hint expires,
-  // so a long wait costs a handful of instructions instead of a poll every few dozen cycles (nanosleep with small
-  // arguments was measured to return after ~20 ns: ~440 polls per tile from the three single-thread roles)
+// Polite wait for the roles that are normally far ahead of the activation warps (producers, MMA issuer of the narrow
+// layers, epilogue): they wait most of a tile, and whatever they execute meanwhile comes out of the issue slots of the
+// activation warps on the same scheduler.  try_wait with a suspend-time hint was measured to return after ~20 ns
+// whatever the hint (ncu, round 1: ~140 poll iterations of 4 instructions per role and tile, 20 % of all issued
+// instructions of a narrow layer), so the loop sleeps with a plain nanosleep between non-blocking tests: one test per
+// `ns` nanoseconds.  Every one of these hand-overs has at least a ring slot (one chunk or tile) of slack, far more than
+// the worst-case wake-up delay of one sleep.
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
-  const uint32_t hint = ns * 20u;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t ns) {
+  if (mbar_test_wait(bar, parity)) return;
+#pragma unroll 1
   for (;;) {
-    asm volatile(
-        "{\n\t.reg .pred P1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, P1;\n\t}\n" : "=r"(done) : "r"(bar), "r"(parity), "r"(hint) : "memory");
-    if (done) break;
+    asm volatile("nanosleep.u32 %0;" ::"r"(ns) : "memory");
+    if (mbar_test_wait(bar, parity)) break;
   }
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
@@ -530,7 +537,7 @@ __device__ __forceinline__ void epilogue_fir_t(const TcArgs& a, float* bias_s, c
         }
       }
     }
-    if (q == 0) mbar_wait_relaxed(bar_accfull0 + 8 * as, ause & 1, 100);
+    if (q == 0) mbar_wait_relaxed(bar_accfull0 + 8 * as, ause & 1, a.Cin <= 96 ? 600u : 120u);
     asm volatile("bar.sync 2, 128;" ::: "memory");
     tc_fence_after();
     const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * n_tile);
@@ -735,7 +742,7 @@ __device__ __forceinline__ void epilogue_pipe_t(const TcArgs& a, float* bias_s, 
 #pragma unroll 1
     for (int s = 0; s < LA; ++s) issue(s);
     prefetch_tile(w + gridDim.x);
-    if (q == 0) mbar_wait_relaxed(bar_accfull0 + 8 * as, ause & 1, 100);
+    if (q == 0) mbar_wait_relaxed(bar_accfull0 + 8 * as, ause & 1, a.Cin <= 96 ? 600u : 120u);
     asm volatile("bar.sync 2, 128;" ::: "memory");
     tc_fence_after();
     const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * n_tile);
@@ -841,7 +848,7 @@ __device__ __forceinline__ void epilogue_up(const TcArgs& a, float* bias_s, cons
     const int cgn0 = nt * (n_tile >> 3);
     const int ng = min(n_tile >> 3, ncg - cgn0);                      // live column groups of this tile
     const int r0 = cgn0 / gpp, cg0 = cgn0 - r0 * gpp;                 // phase / channel group of the first one
-    if (q == 0) mbar_wait_relaxed(bar_accfull0 + 8 * as, ause & 1, 100);
+    if (q == 0) mbar_wait_relaxed(bar_accfull0 + 8 * as, ause & 1, a.Cin <= 96 ? 600u : 120u);
     asm volatile("bar.sync 2, 128;" ::: "memory");
     tc_fence_after();
     const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * n_tile);
@@ -912,6 +919,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmr,
          const __grid_constant__ CUtensorMap tmq, const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tile = a.n_tile, n_tiles = a.n_tiles;
 
@@ -982,6 +990,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int total_tiles = prefix[a.B] * n_tiles;
+  pdl_wait();          // the prologue above only read launch constants (lengths, parameters); activations from here on
 
   if (warp < NW_ACT) {
     // ===================== activation warps =====================
@@ -1097,7 +1106,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
           int b, t0, nt;
           cur.locate(w, n_tiles, b, t0, nt);
           for (int c = 0; c < NCH; ++c) {
-            mbar_wait_relaxed(BAR_XEMPTY(xb), xph ^ 1, 200);
+            mbar_wait_relaxed(BAR_XEMPTY(xb), xph ^ 1, 400);
             // activated layers never read the channel groups past C_in (their warps skip); plain convs feed the
             // x tile to the MMA as it is and need the TMA zero fill of those groups
             const int lg = ACT ? min(4, (a.Cin >> 3) - c * 4) : 4;
@@ -1190,7 +1199,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
           uint32_t accflag = 0;
           for (int c = 0; c < NCH; ++c) {
             // narrow layers are bound by the activation warps' issue slots: the issuer sleeps between polls there
-            if (lazy) mbar_wait_relaxed(barF + 8 * rb, rph, 200);
+            if (lazy) mbar_wait_relaxed(barF + 8 * rb, rph, 300);
             else mbar_wait(barF + 8 * rb, rph);
             tc_fence_after();
             const uint32_t aU = ring0 + (uint32_t)rb * ringU;

@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <string>
@@ -31,6 +32,23 @@ int fail(int status, const char* fmt, ...) {
   va_end(ap);
   last_error() = buf;
   return status;
+}
+
+// PDL on the decode's launches: default on; BVG_PDL=0 or bvg_set_pdl(0) turns the launch attribute off
+static std::atomic<int> g_pdl{-1};
+bool pdl_enabled() {
+  int v = g_pdl.load();
+  if (v < 0) {
+    const char* e = getenv("BVG_PDL");
+    v = (!e || atoi(e) != 0) ? 1 : 0;
+    g_pdl = v;
+  }
+  return v != 0;
+}
+int set_pdl(int on) {
+  const int old = pdl_enabled() ? 1 : 0;
+  g_pdl = on ? 1 : 0;
+  return old;
 }
 
 cudaError_t func_attr_once(const void* fn, cudaFuncAttribute attr, int value) {
@@ -237,6 +255,7 @@ static int ensure_ws(bvg_plan* p, size_t bytes_per_buf) {
     BVG_CUDA(cudaMemset(p->ws[i], 0, bytes_per_buf));
   }
   p->ws_bytes = bytes_per_buf;
+  ++p->alloc_gen;
   return 0;
 }
 
@@ -252,6 +271,7 @@ int upload_lengths(bvg_plan* p, const int32_t* lengths, int B, int Tmax, cudaStr
     }
     BVG_CUDA(cudaMalloc((void**)&p->d_len, sizeof(int) * B));
     p->d_len_cap = B;
+    ++p->alloc_gen;
   }
   const int s = p->len_slot;
   p->len_slot = (s + 1) % kLenSlots;
@@ -274,11 +294,11 @@ int compute_cond_bias(bvg_plan* p, const float* spk_emb, int B, cudaStream_t st)
     if (p->condb) BVG_CUDA(cudaFree(p->condb));
     BVG_CUDA(cudaMalloc((void**)&p->condb, need_elems * sizeof(float)));
     p->condb_elems = need_elems;
+    ++p->alloc_gen;
   }
   const int warps = B * p->cond_total;
-  k_cond_bias<<<ceil_div(warps * 32, 256), 256, 0, st>>>(p->cond_W, p->cond_b, spk_emb, p->condb,
-                                                         p->cond_total, p->cfg.speaker_embedding_dim, B);
-  BVG_CUDA(cudaGetLastError());
+  BVG_CUDA(launch_k(k_cond_bias, dim3(ceil_div(warps * 32, 256)), dim3(256), 0, st, false, (const float*)p->cond_W,
+                    (const float*)p->cond_b, spk_emb, p->condb, p->cond_total, p->cfg.speaker_embedding_dim, B));
   ++p->last_launches;
   return 0;
 }
@@ -589,6 +609,14 @@ int bvg_decode(bvg_plan* p, const void* latent, int latent_dtype, const int32_t*
   int rc;
   if ((rc = upload_lengths(p, lengths, B, Tmax, st, &d_len))) return rc;
   if ((rc = compute_cond_bias(p, spk_emb, B, st))) return rc;
+  if (precision != BVG_PREC_F32 && precision != BVG_PREC_BF16) return fail(BVG_ERR_ARG, "bvg_decode: unknown precision %d", precision);
+  if (p->ws_prec != precision) {
+    // the four workspace buffers are shared by both paths: fp32 words read as bf16 pairs include NaN / Inf patterns,
+    // which the bf16 kernels may multiply by zero weights (rows past an utterance's end) — start from zeros instead
+    for (int i = 0; i < 4; ++i)
+      if (p->ws[i]) BVG_CUDA(cudaMemsetAsync(p->ws[i], 0, p->ws_bytes, st));
+    p->ws_prec = precision;
+  }
   if (precision == BVG_PREC_F32)
     return decode_f32(p, latent, latent_dtype, d_len, B, Tmax, wav_out, wav_dtype, st);
   if (precision == BVG_PREC_BF16)
@@ -730,6 +758,8 @@ int bvg_set_tc_fir_max_channels(int max_c) { return bvg::tc_set_fir_max_c(max_c)
 int bvg_set_tc_narrow_max_channels(int max_c) { return bvg::tc_set_nar_max_c(max_c); }
 int bvg_set_tc_split_min_channels(int min_c) { return bvg::tc_set_split_min_c(min_c); }
 int bvg_set_tc_residual_mma(int on) { return bvg::tc_set_residual_mma(on); }
+int bvg_set_graphs(int on) { return bvg::tc_set_graphs(on); }
+int bvg_set_pdl(int on) { return bvg::set_pdl(on); }
 
 int bvg_plan_read_profile(bvg_plan* p, bvg_profile* out) {
   BVG_REQUIRE(p && out, "bvg_plan_read_profile: null argument");

@@ -77,6 +77,28 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 #define BVG_DBGBIT(a, bit) false
 #endif
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may be
+// scheduled while its predecessor in the stream is still running; it calls pdl_wait() before it touches anything the
+// predecessor wrote (or writes anything the predecessor may still read), and every kernel calls
+// pdl_launch_dependents() first thing so that its successor's CTAs can take idle SMs and run their prologue (TMEM
+// allocation, mbarrier init, tile prefix table, tensor-map prefetch) early.  Both are no-ops in a plain launch.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // cudaFuncSetAttribute is per (function, device): a plan per GPU in one process, or a module moved between GPUs,
 // must opt every device in.  Thread-safe; returns a cudaError_t.
 cudaError_t func_attr_once(const void* fn, cudaFuncAttribute attr, int value);

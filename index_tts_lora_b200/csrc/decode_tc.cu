@@ -97,6 +97,8 @@ __global__ void k_tc_params(const float* a, const float* invb, float* a2, float*
 // blocked bf16 [B][C/8][Tmax][8], zero beyond each utterance's length.
 __global__ void k_latent_blk(const void* __restrict__ lat, int dtype, __nv_bfloat16* __restrict__ out, int C,
                              int Tmax, const int* __restrict__ lengths) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.z, cg = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= Tmax) return;
@@ -136,9 +138,11 @@ __global__ void __launch_bounds__(256) k_conv_post_blk(const __nv_bfloat16* __re
                                                        int groups, int K, int Tstride, const int* __restrict__ lengths,
                                                        int rate) {
   __shared__ float ws[8 * 16 * 16];                 // [C][K] tap weights, C <= 128, K <= 16
+  pdl_launch_dependents();
   const int C = groups * 8;
   for (int i = threadIdx.x; i < C * K; i += blockDim.x) ws[i] = wp[i];   // wp is [Cin][K][Cout = 1]
   __syncthreads();
+  pdl_wait();
   const int b = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= Tstride) return;
@@ -174,6 +178,14 @@ struct TcLayer {
   __nv_bfloat16* idw = nullptr;   // identity tiles (square layers only): residual add on the tensor core
 };
 
+struct GraphEntry {                 // one captured tc_middle (see tc_decode)
+  int B = 0, Tmax = 0;
+  bool ragged = false, failed = false;
+  std::vector<int32_t> lens;
+  cudaGraphExec_t exec = nullptr;
+  int launches = 0;
+};
+
 struct TcPlan {
   TcLayer pre;
   TcLayer ups[kMaxStages];
@@ -193,6 +205,9 @@ struct TcPlan {
   cudaEvent_t ev_fork = nullptr, ev_last[BVG_MAX_KERNELS] = {};
   std::map<std::tuple<const void*, int, int, int, int, int>, CUtensorMap> maps;
   std::vector<void*> owned;
+  std::vector<GraphEntry> graphs;
+  cudaStream_t cap_stream = nullptr;
+  unsigned long long graph_gen = 0;
 };
 
 static void pick_tile(int Cout, int* n_tile, int* n_tiles) {
@@ -313,6 +328,8 @@ void tc_plan_free(bvg_plan* p) {
   for (void* q : t->cbuf) if (q) cudaFree(q);
   for (void* q : t->zbuf) if (q) cudaFree(q);
   for (cudaStream_t q : t->aux) if (q) cudaStreamDestroy(q);
+  for (GraphEntry& g : t->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (t->cap_stream) cudaStreamDestroy(t->cap_stream);
   if (t->ev_fork) cudaEventDestroy(t->ev_fork);
   for (cudaEvent_t e : t->ev_last) if (e) cudaEventDestroy(e);
   delete t;
@@ -423,8 +440,7 @@ static int launch_inst_rm(const CUtensorMap& map, const CUtensorMap& mapr, const
   // roles (local memory) and the few global scalars: ask for the smallest carve-out that holds this launch.
   const int want = std::min(100, (smem + 1024) * 100 / (228 * 1024) + 1);
   BVG_CUDA(func_attr_once((const void*)kern, cudaFuncAttributePreferredSharedMemoryCarveout, want));
-  kern<<<grid, NTHREADS, smem, st>>>(map, mapr, mapq, a);
-  BVG_CUDA(cudaGetLastError());
+  BVG_CUDA(launch_k(kern, grid, dim3(NTHREADS), (size_t)smem, st, true, map, mapr, mapq, a));
   return 0;
 }
 
@@ -543,7 +559,7 @@ static int launch_act_blk(bvg_plan* p, const ConvW& cw, const ActW* aw, const Tc
   dim3 grid((unsigned)std::min<long long>((units + AB_WARPS - 1) / AB_WARPS, 2LL * sms));
   const double samples = (p ? p->cur_sum_frames : 0.0) * q.rate;
   prof_begin(p, st, q.cls, 0.0, samples * 2.0 * 2.0 * cw.Cin);
-  k_act_blk<<<grid, AB_WARPS * 32, smem, st>>>(b);
+  BVG_CUDA(launch_k(k_act_blk, grid, dim3(AB_WARPS * 32), (size_t)smem, st, true, b));
   prof_end(p, st);
   BVG_CUDA(cudaGetLastError());
   if (p) ++p->last_launches;
@@ -753,6 +769,7 @@ static int tc_prepare(bvg_plan* p, TcPlan* t, int B, int Fs) {
     BVG_CUDA(cudaMalloc(&t->lat_blk, lat_need));
     BVG_CUDA(cudaMemset(t->lat_blk, 0, lat_need));
     t->lat_bytes = lat_need;
+    ++p->alloc_gen;
     t->maps.clear();
   }
   if (buf_bytes > t->cbuf_bytes) {
@@ -764,6 +781,7 @@ static int tc_prepare(bvg_plan* p, TcPlan* t, int B, int Fs) {
       BVG_CUDA(cudaMemset(qb, 0, buf_bytes));       // see ensure_ws: stale rows must be finite
     }
     t->cbuf_bytes = buf_bytes;
+    ++p->alloc_gen;
     t->maps.clear();
   }
   // scratch of the split layers: the largest split stage (channels x rows), one buffer per block stream
@@ -780,6 +798,7 @@ static int tc_prepare(bvg_plan* p, TcPlan* t, int B, int Fs) {
       BVG_CUDA(cudaMemset(qb, 0, z_bytes));
     }
     t->zbuf_bytes = z_bytes;
+    ++p->alloc_gen;
     t->maps.clear();
   }
   if (!t->ev_fork) {
@@ -791,16 +810,20 @@ static int tc_prepare(bvg_plan* p, TcPlan* t, int B, int Fs) {
 }
 
 // latent -> blocked bf16 -> conv_pre + cond_layer add (models.py:222-228)
+// parts: 1 = the re-blocking kernel (the only one that touches the caller's latent), 2 = conv_pre, 3 = both
 static int tc_pre(bvg_plan* p, TcPlan* t, const void* latent, int latent_dtype, __nv_bfloat16* out, int B, int Fs,
-                  const int32_t* h_len, const int* d_len, cudaStream_t st) {
+                  const int32_t* h_len, const int* d_len, cudaStream_t st, int parts = 3) {
   int rc;
   CUtensorMap map;
   dim3 grid(ceil_div(Fs, 128), p->cfg.gpt_dim / 8, B);
+  if (parts & 1) {
   prof_begin(p, st, 2, 0.0, (double)B * Fs * p->cfg.gpt_dim * 6.0);
-  k_latent_blk<<<grid, 128, 0, st>>>(latent, latent_dtype, (__nv_bfloat16*)t->lat_blk, p->cfg.gpt_dim, Fs, d_len);
+  BVG_CUDA(launch_k(k_latent_blk, grid, dim3(128), 0, st, true, latent, latent_dtype, (__nv_bfloat16*)t->lat_blk, p->cfg.gpt_dim, Fs, d_len));
   prof_end(p, st);
   BVG_CUDA(cudaGetLastError());
   ++p->last_launches;
+  }
+  if (!(parts & 2)) return 0;
   if ((rc = get_map(t, t->lat_blk, p->cfg.gpt_dim, Fs, B, &map))) return rc;
   TcLaunch q;   // plain conv: the TMA tile feeds the MMA directly
   q.x = t->lat_blk; q.out = out; q.bias_b = p->condb + p->cond_off[0]; q.bias_b_stride = p->cond_total;
@@ -884,13 +907,18 @@ static int tc_stage(bvg_plan* p, TcPlan* t, int i, const StageIO& io, cudaStream
 // activation_post + conv_post + tanh (models.py:248-250): the streaming Activation1d kernel, then a 24 -> 1 channel conv
 // + tanh that reads its bf16 rows.  (The SIMT kernel this replaces took 1.1 ms of a 25 ms step; it still serves the
 // shapes this one does not cover.)  `cur` may point into the middle of a stage buffer (time-split windows).
-static int tc_post(bvg_plan* p, TcPlan* t, const __nv_bfloat16* cur, void* wav_out, int wav_dtype, int B, int Tmax,
-                   const int* d_len, cudaStream_t st) {
-  int rc;
+static bool post_is_split(const bvg_plan* p) {
   static const bool old_post = getenv("BVG_SIMT_POST") != nullptr;
   const int S = p->n_stages, Cp = p->C[S], Kp = p->conv_post.K;
-  if (old_post || Cp % 8 != 0 || Cp > 128 || Kp > 16 || p->conv_post.Cout != 1)
-    return simt_post_blk(p, cur, wav_out, wav_dtype, B, Tmax, d_len, st);
+  return !(old_post || Cp % 8 != 0 || Cp > 128 || Kp > 16 || p->conv_post.Cout != 1);
+}
+
+// parts: 1 = activation_post (plan-owned buffers only), 2 = conv_post + tanh (writes the caller's waveform), 3 = both
+static int tc_post(bvg_plan* p, TcPlan* t, const __nv_bfloat16* cur, void* wav_out, int wav_dtype, int B, int Tmax,
+                   const int* d_len, cudaStream_t st, int parts = 3) {
+  int rc;
+  const int S = p->n_stages, Cp = p->C[S], Kp = p->conv_post.K;
+  if (!post_is_split(p)) return (parts & 2) ? simt_post_blk(p, cur, wav_out, wav_dtype, B, Tmax, d_len, st) : 0;
   const int Ts = Tmax * p->rate[S];
   __nv_bfloat16* zpost = (__nv_bfloat16*)t->cbuf[0];        // the block buffers are idle after the last stage
   TcLayer Lp;
@@ -899,15 +927,61 @@ static int tc_post(bvg_plan* p, TcPlan* t, const __nv_bfloat16* cur, void* wav_o
   TcLaunch qp;
   qp.x = cur; qp.zbuf = zpost; qp.B = B; qp.Tstride = Ts; qp.rate = p->rate[S]; qp.d_len = d_len; qp.cls = 3;
   qp.sm_count = p->sm_count;
-  if ((rc = launch_act_blk(p, cwp, &p->act_post, Lp, qp, st))) return rc;
+  if ((parts & 1) && (rc = launch_act_blk(p, cwp, &p->act_post, Lp, qp, st))) return rc;
+  if (!(parts & 2)) return 0;
   dim3 gridp(ceil_div(Ts, 256), B);
   prof_begin(p, st, 3, 2.0 * Cp * Kp * p->cur_sum_frames * p->rate[S], (2.0 * Cp + 4.0) * p->cur_sum_frames * p->rate[S]);
-  k_conv_post_blk<<<gridp, 256, 0, st>>>(zpost, p->conv_post.wp, p->conv_post.bias, wav_out, wav_dtype, Cp / 8, Kp, Ts, d_len,
-                                        p->rate[S]);
+  BVG_CUDA(launch_k(k_conv_post_blk, gridp, dim3(256), 0, st, true, (const __nv_bfloat16*)zpost, (const float*)p->conv_post.wp,
+                    (const float*)p->conv_post.bias, wav_out, wav_dtype, Cp / 8, Kp, Ts, d_len, p->rate[S]));
   prof_end(p, st);
   BVG_CUDA(cudaGetLastError());
   ++p->last_launches;
   return 0;
+}
+
+// Everything of a decode that only touches plan-owned buffers: conv_pre, the six stages, activation_post.
+static int tc_middle(bvg_plan* p, TcPlan* t, int B, int Tmax, const int32_t* h_len, const int* d_len, cudaStream_t st) {
+  int rc;
+  __nv_bfloat16* cur = (__nv_bfloat16*)p->ws[0];
+  if ((rc = tc_pre(p, t, nullptr, 0, cur, B, Tmax, h_len, d_len, st, 2))) return rc;
+  for (int i = 0; i < p->n_stages; ++i) {
+    StageIO io;
+    io.cur = cur; io.xin = (__nv_bfloat16*)p->ws[1]; io.xs = cur;   // cur is dead once the ConvTranspose1d consumed it
+    io.B = B; io.Fs = Tmax; io.h_len = h_len; io.d_len = d_len;
+    if ((rc = tc_stage(p, t, i, io, st))) return rc;
+  }
+  return tc_post(p, t, cur, nullptr, 0, B, Tmax, d_len, st, 1);
+}
+
+// CUDA-graph replay of tc_middle.  A decode is 118 launches on three streams; on short utterances the launches, the
+// fork / join events and the grid-launch latency between dependent kernels are a large part of the wall time.  The
+// middle of a decode only reads and writes plan-owned buffers at fixed addresses, so for a given (B, Tmax, lengths) it
+// is the same launch sequence every time: it is stream-captured (on a plan-owned stream: the caller's may be the
+// legacy default stream, which cannot be captured) the SECOND time a shape is seen, instantiated, and replayed on the
+// caller's stream afterwards.  The programmatic-dependent-launch edges survive the capture.  The kernels that touch
+// the caller's pointers (latent re-blocking, speaker-conditioning GEMV, conv_post) stay ordinary launches around it.
+static std::atomic<int> g_graphs{-1};
+int tc_set_graphs(int on) {
+  const int cur = g_graphs.load(), old = cur < 0 ? 1 : cur;
+  g_graphs = on ? 1 : 0;
+  return old;
+}
+static bool graphs_on() {
+  if (g_graphs < 0) {
+    const char* e = getenv("BVG_GRAPHS");
+    g_graphs = (!e || atoi(e) != 0) ? 1 : 0;
+  }
+  return g_graphs != 0;
+}
+constexpr size_t kMaxGraphs = 64;
+
+static GraphEntry* find_graph(TcPlan* t, int B, int Tmax, const int32_t* h_len) {
+  for (GraphEntry& g : t->graphs) {
+    if (g.B != B || g.Tmax != Tmax || g.ragged != (h_len != nullptr)) continue;
+    if (h_len && memcmp(g.lens.data(), h_len, sizeof(int32_t) * B) != 0) continue;
+    return &g;
+  }
+  return nullptr;
 }
 
 int tc_decode(bvg_plan* p, const void* latent, int latent_dtype, const int32_t* h_len, const int* d_len, int B,
@@ -916,15 +990,53 @@ int tc_decode(bvg_plan* p, const void* latent, int latent_dtype, const int32_t* 
   if (!t) return fail(BVG_ERR_STATE, "tcgen05 path: weights not packed");
   int rc;
   if ((rc = tc_prepare(p, t, B, Tmax))) return rc;
-  __nv_bfloat16* cur = (__nv_bfloat16*)p->ws[0];
-  if ((rc = tc_pre(p, t, latent, latent_dtype, cur, B, Tmax, h_len, d_len, st))) return rc;
-  for (int i = 0; i < p->n_stages; ++i) {
-    StageIO io;
-    io.cur = cur; io.xin = (__nv_bfloat16*)p->ws[1]; io.xs = cur;   // cur is dead once the ConvTranspose1d consumed it
-    io.B = B; io.Fs = Tmax; io.h_len = h_len; io.d_len = d_len;
-    if ((rc = tc_stage(p, t, i, io, st))) return rc;
+  if (t->graph_gen != p->alloc_gen) {          // some buffer moved since the graphs were captured
+    for (GraphEntry& g : t->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    t->graphs.clear();
+    t->graph_gen = p->alloc_gen;
   }
-  return tc_post(p, t, cur, wav_out, wav_dtype, B, Tmax, d_len, st);
+  __nv_bfloat16* cur = (__nv_bfloat16*)p->ws[0];
+  if ((rc = tc_pre(p, t, latent, latent_dtype, cur, B, Tmax, h_len, d_len, st, 1))) return rc;
+  bool done = false;
+  if (graphs_on() && !p->profiling && post_is_split(p)) {
+    GraphEntry* g = find_graph(t, B, Tmax, h_len);
+    if (!g) {                                   // first sighting: run it eagerly (sets function attributes, fills caches)
+      if (t->graphs.size() >= kMaxGraphs) {
+        if (t->graphs.front().exec) cudaGraphExecDestroy(t->graphs.front().exec);
+        t->graphs.erase(t->graphs.begin());
+      }
+      GraphEntry e;
+      e.B = B; e.Tmax = Tmax; e.ragged = h_len != nullptr;
+      if (h_len) e.lens.assign(h_len, h_len + B);
+      t->graphs.push_back(std::move(e));
+    } else if (!g->exec && !g->failed) {        // second sighting: capture
+      if (!t->cap_stream) BVG_CUDA(cudaStreamCreateWithFlags(&t->cap_stream, cudaStreamNonBlocking));
+      const int before = p->last_launches;
+      cudaGraph_t graph = nullptr;
+      cudaError_t ce = cudaStreamBeginCapture(t->cap_stream, cudaStreamCaptureModeThreadLocal);
+      if (ce == cudaSuccess) {
+        rc = tc_middle(p, t, B, Tmax, h_len, d_len, t->cap_stream);
+        ce = cudaStreamEndCapture(t->cap_stream, &graph);
+        if (rc == 0 && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&g->exec, graph, 0);
+        else if (ce == cudaSuccess) ce = cudaErrorUnknown;
+        if (graph) cudaGraphDestroy(graph);
+      }
+      g->launches = p->last_launches - before;
+      p->last_launches = before;
+      if (ce != cudaSuccess || !g->exec) {       // capture is an optimisation: fall back to plain launches for this shape
+        g->exec = nullptr;
+        g->failed = true;
+        cudaGetLastError();
+      }
+    }
+    if (g && g->exec) {
+      BVG_CUDA(cudaGraphLaunch(g->exec, st));
+      p->last_launches += g->launches;
+      done = true;
+    }
+  }
+  if (!done && (rc = tc_middle(p, t, B, Tmax, h_len, d_len, st))) return rc;
+  return tc_post(p, t, cur, wav_out, wav_dtype, B, Tmax, d_len, st, 2);
 }
 
 // ------------------------------------------------------------------------------ time split (P2P)

@@ -438,6 +438,8 @@ __global__ void k_pack_convtr_w(const float* w, float* wp, int Cin, int Cout, in
 __global__ void k_cond_bias(const float* __restrict__ Wc, const float* __restrict__ bc,
                             const float* __restrict__ emb, float* __restrict__ condb, int Ctot,
                             int D, int B) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= Ctot * B) return;

@@ -57,6 +57,7 @@ struct bvg_plan {
   // grow-only workspace
   void* ws[4] = {nullptr, nullptr, nullptr, nullptr};
   size_t ws_bytes = 0;  // per buffer
+  int ws_prec = -1;     // precision path that last wrote the workspace
   float* condb = nullptr;
   size_t condb_elems = 0;
   int* d_len = nullptr;
@@ -70,6 +71,7 @@ struct bvg_plan {
   float* st_emb = nullptr; size_t st_emb_elems = 0;
   void* st_wav = nullptr;  size_t st_wav_bytes = 0;
 
+  unsigned long long alloc_gen = 1;   // bumped whenever a plan-owned device buffer is re-allocated (captured graphs die)
   int last_launches = 0;
   double cur_sum_frames = 0;   // sum of valid latent frames of the decode being enqueued
   bool profiling = false;

@@ -252,3 +252,35 @@ def test_infer_py_load_sequence_and_forward(branch):
         snr = _snr(ref, got)
         print("infer.py load sequence,", branch, "SNR", snr)
         assert snr > 35.0, snr
+
+
+# ----------------------------------------------------------------------------- launch latency: PDL + CUDA graphs
+def test_graph_replay_and_pdl_are_bit_identical(real):
+    """bvg_set_graphs / bvg_set_pdl change how the 118 launches of a decode reach the GPU, not what they compute: the
+    third decode of a shape (replayed from the captured graph, programmatic edges kept) must equal the plain-launch
+    decode bit for bit — uniform batch, ragged batch, shapes interleaved, new output / input tensors every call."""
+    from index_tts_lora_b200 import synth, _lib
+    m, h = real["m"], real["h"]
+    lib = _lib.load()
+    dev = _dev()
+    m.precision = "bf16"
+    emb = real["emb"].to(dev)
+    cases = [([40, 40], None), ([57, 31, 8], [57, 31, 8]), ([157], None)]
+    lats = [synth.synth_latent(len(c[0]), max(c[0]), h.gpt_dim, seed=11 + i).to(dev).to(torch.bfloat16)
+            for i, c in enumerate(cases)]
+    og, op = lib.bvg_set_graphs(0), lib.bvg_set_pdl(0)
+    try:
+        ref = [m.decode(x.clone(), emb, lengths=c[1], out_dtype=torch.float32).clone() for x, c in zip(lats, cases)]
+        lib.bvg_set_pdl(1)
+        pdl = [m.decode(x.clone(), emb, lengths=c[1], out_dtype=torch.float32).clone() for x, c in zip(lats, cases)]
+        lib.bvg_set_graphs(1)
+        outs = []
+        for rep in range(4):                       # 1st eager, 2nd captures, 3rd / 4th replay; shapes interleaved
+            outs = [m.decode(x.clone(), emb, lengths=c[1], out_dtype=torch.float32).clone() for x, c in zip(lats, cases)]
+    finally:
+        lib.bvg_set_graphs(og)
+        lib.bvg_set_pdl(op)
+    torch.cuda.synchronize()
+    for r, a, b in zip(ref, pdl, outs):
+        assert torch.equal(r, a), "PDL changed the result"
+        assert torch.equal(r, b), "graph replay changed the result"

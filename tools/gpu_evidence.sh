@@ -8,15 +8,20 @@ BVG_PROF_DUMP=1 timeout -s KILL 200 python tools/per_launch.py 2> gpurun_out/${T
 timeout -s KILL 200 $P > gpurun_out/${TAG}_plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/${TAG}_plain.log; exit 1; }
 timeout -s KILL 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
     -k regex:k_amp_tc -s 115 -c 115 --csv --log-file gpurun_out/${TAG}_launches_time_dram.csv $P > /dev/null 2>&1
-cap() {  # name, kernel regex, skip
+cap() {  # name, kernel regex, skip, tiles per launch (for the per-role table).  The .ncu-rep files are summarised here and
+  # deleted (gpurun brings back at most 64 MiB); KEEP_REP=1 keeps them
   timeout -s KILL 400 ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c 1 -f -o gpurun_out/${TAG}_$1 $P > gpurun_out/${TAG}_$1.log 2>&1
+  python tools/ncu_summary.py gpurun_out/${TAG}_$1.ncu-rep > gpurun_out/${TAG}_ncu_$1.txt 2>&1
+  python tools/ncu_roles.py gpurun_out/${TAG}_$1.ncu-rep $4 >> gpurun_out/${TAG}_ncu_$1.txt 2>&1
+  [ "$KEEP_REP" = "1" ] || rm -f gpurun_out/${TAG}_$1.ncu-rep
 }
-cap s0k3A k_amp_tc 117
-cap s0k7A k_amp_tc 123
-cap s0k11A k_amp_tc 129
-cap s1k3A k_amp_tc 136
-cap s3k7A k_amp_tc 180
-cap s5k3B k_amp_tc 213
-cap s5k11B k_amp_tc 229
-cap actblk k_act_blk 1
-ls -la gpurun_out/${TAG}_*.ncu-rep | wc -l
+# tiles per launch: 16 utterances x ceil(234 * rate / 256) time tiles x column tiles
+cap s0k3A k_amp_tc 117 192
+cap s0k7A k_amp_tc 123 192
+cap s0k11A k_amp_tc 129 192
+cap s1k3A k_amp_tc 136 480
+cap s3k7A k_amp_tc 180 3744
+cap s5k3B k_amp_tc 213 14976
+cap s5k11B k_amp_tc 229 14976
+cap actblk k_act_blk 1 1
+ls gpurun_out/${TAG}_ncu_*.txt | wc -l; du -sh gpurun_out

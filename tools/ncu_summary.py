@@ -22,7 +22,9 @@ for h, u, v in zip(hdr, units, vals):
         print(f"{h} = {v} {u}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
-h2 = rows[1]; data = rows[2:]
+hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"]          # one block per captured kernel: take the first
+h2 = rows[hi[0]]
+data = [r for r in rows[hi[0] + 1:(hi[1] - 1 if len(hi) > 1 else len(rows))] if len(r) == len(h2)]
 isrc, isamp, iex = h2.index("Source"), h2.index("# Samples"), h2.index("Instructions Executed")
 tot = sum(int(x[isamp] or 0) for x in data)
 byop, exe = Counter(), Counter()

@@ -11,7 +11,8 @@ from index_tts_lora_b200.models import BigVGAN
 torch.set_grad_enabled(False)
 dev = torch.device("cuda:0"); h = default_config()
 m = BigVGAN(h); m.load_state_dict(synth.synth_state_dict(m.state_dict(), seed=1234, profile="init")); m = m.to(dev); m.remove_weight_norm(); m.eval(); m.precision = "bf16"
-lat = synth.synth_latent(16, 234, h.gpt_dim, seed=0).to(dev).to(torch.bfloat16)
+B = int(os.environ.get("PL_B", "16")); F = int(os.environ.get("PL_F", "234"))
+lat = synth.synth_latent(B, F, h.gpt_dim, seed=0).to(dev).to(torch.bfloat16)
 emb = m.speaker_embedding(synth.synth_mel(1, 300, h.num_mels, seed=1).to(dev))
 lib = _lib.load(); plan = m._ensure_plan(dev)
 if len(sys.argv) > 1: lib.bvg_set_tc_split_min_channels(int(sys.argv[1]))
