@@ -972,11 +972,12 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
     if (lane == 0) prefix[0] = 0;
   }
   if (warp == NW_ACT && lane == 0) {
-    for (int i = 0; i < NX_MAX; ++i) { mbar_init(BAR_XFULL(i), 1); mbar_init(BAR_XEMPTY(i), ACT ? NW_ACT : 1); }
-    for (int i = 0; i < NZ_MAX; ++i) { mbar_init(BAR_ZFULL(i), NW_ACT); mbar_init(BAR_ZEMPTY(i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(BAR_ACCFULL(i), 1); mbar_init(BAR_ACCEMPTY(i), 4); }
-    for (int i = 0; i < R_RING; ++i) { mbar_init(BAR_RFULL(i), 1); mbar_init(BAR_REMPTY(i), 1); }
-    for (int i = 0; i < W_STAGES_MAX; ++i) { mbar_init(BAR_WFULL(i), 1); mbar_init(BAR_WEMPTY(i), 1); }
+    // two MMA issuer warps (one per M block): every "the MMAs that read this are done" barrier takes two commits
+    for (int i = 0; i < NX_MAX; ++i) { mbar_init(BAR_XFULL(i), 1); mbar_init(BAR_XEMPTY(i), ACT ? NW_ACT : 2); }
+    for (int i = 0; i < NZ_MAX; ++i) { mbar_init(BAR_ZFULL(i), NW_ACT); mbar_init(BAR_ZEMPTY(i), 2); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR_ACCFULL(i), 2); mbar_init(BAR_ACCEMPTY(i), 4); }
+    for (int i = 0; i < R_RING; ++i) { mbar_init(BAR_RFULL(i), 1); mbar_init(BAR_REMPTY(i), 2); }
+    for (int i = 0; i < W_STAGES_MAX; ++i) { mbar_init(BAR_WFULL(i), 1); mbar_init(BAR_WEMPTY(i), 2); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmx)) : "memory");
   }
@@ -1169,13 +1170,17 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
           }
         }
       }
-    } else if (warp == NW_ACT + 2) {
-      // ===================== MMA issuer =====================
-      // One thread, 32 registers: everything loop-carried is kept to a minimum (one operand ring index instead of
-      // separate x / z cursors, descriptors rebuilt from 32-bit address units) because a spilled value costs an L2
-      // round trip here — shared memory leaves the SM little L1 — and this thread is the serial link between the
-      // activation warps and the epilogue.
+    } else {
+      // ===================== MMA issuers =====================
+      // Two warps, one per M block (accumulator) of the tile: an issuer is a single thread's worth of dependent
+      // uniform-datapath code — ~9 instructions per tcgen05.mma at ~14 cycles each (ncu, stage 5, k = 11: the narrow
+      // many-tap layers were bound by exactly this loop, their activation warps spinning on full z slots) — and the two
+      // accumulators are independent, so each warp issues its own block's MMAs with its TMEM address and instruction
+      // descriptor loop-invariant.  One issuer per accumulator keeps the summation order, hence the result, fixed.
+      // 32 registers: everything loop-carried is kept to a minimum (one operand ring index instead of separate x / z
+      // cursors, descriptors rebuilt from 32-bit address units) because a spilled value costs an L2 round trip here.
       {
+        const uint32_t mbk = (uint32_t)(warp - (NW_ACT + 2));   // my M block: rows [128 mbk, 128 mbk + 128)
         const uint32_t leader = elect_one();      // the whole warp walks the loop; one lane issues
         const uint32_t idesc = make_idesc_bf16(128, n_tile);
         const uint32_t lboA = (ACT ? ZR : XRA) * 16;
@@ -1195,7 +1200,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
           const int as = (nacc == 2) ? (it & 1) : 0;
           mbar_wait(BAR_ACCEMPTY(as), ((((nacc == 2) ? (it >> 1) : it) & 1) ^ 1));   // epilogue has drained this stage
           tc_fence_after();
-          const uint32_t tm = tmem + (uint32_t)(as * 2 * n_tile);
+          const uint32_t tm = tmem + (uint32_t)(as * 2 * n_tile) + mbk * (uint32_t)n_tile;
           uint32_t accflag = 0;
           for (int c = 0; c < NCH; ++c) {
             // narrow layers are bound by the activation warps' issue slots: the issuer sleeps between polls there
@@ -1209,14 +1214,10 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
               tc_fence_after();
               const uint32_t wU = (s_base + OFF_W + stage * W_STAGE_BYTES) >> 4;
               for (int tj = 0; tj < taps; ++tj) {
-                const uint32_t a0 = aU + (uint32_t)((s * tps + tj) * a.dil);
+                const uint32_t a0 = aU + (uint32_t)((s * tps + tj) * a.dil) + mbk * 128u;
                 const uint32_t b0 = wU + (uint32_t)tj * tileU;
                 umma_bf16_e(leader, tm, hiA | a0, hiB | b0, idesc, accflag);
-                if (!BVG_DBGBIT(a, 1)) {
-                  umma_bf16_e(leader, tm, hiA | (a0 + ksA), hiB | (b0 + ksB), idesc, 1u);
-                  umma_bf16_e(leader, tm + n_tile, hiA | (a0 + 128), hiB | b0, idesc, accflag);
-                  umma_bf16_e(leader, tm + n_tile, hiA | (a0 + 128 + ksA), hiB | (b0 + ksB), idesc, 1u);
-                }
+                if (!BVG_DBGBIT(a, 1)) umma_bf16_e(leader, tm, hiA | (a0 + ksA), hiB | (b0 + ksB), idesc, 1u);
                 accflag = 1u;
               }
               umma_commit_e(leader, BAR_WEMPTY(stage));          // weight stage free once these MMAs retire
@@ -1233,10 +1234,8 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
                 const uint32_t r0 = (s_base + OFF_R + rr * R_SLOT_BYTES) >> 4;
                 const uint32_t b0 = (s_base + OFF_W + stage * W_STAGE_BYTES) >> 4;
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                  umma_bf16_e(leader, tm, hiR | (r0 + ks * (2 * M_TILE)), hiB | (b0 + ks * ksB), idesc, 1u);
-                  umma_bf16_e(leader, tm + n_tile, hiR | (r0 + ks * (2 * M_TILE) + 128), hiB | (b0 + ks * ksB), idesc, 1u);
-                }
+                for (int ks = 0; ks < 2; ++ks)
+                  umma_bf16_e(leader, tm, hiR | (r0 + ks * (2 * M_TILE) + mbk * 128u), hiB | (b0 + ks * ksB), idesc, 1u);
                 umma_commit_e(leader, BAR_WEMPTY(stage));
                 if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
                 umma_commit_e(leader, BAR_REMPTY(rr));
