@@ -261,6 +261,42 @@ int bvg_conv_transpose1d(const float* x, float* y, int B, int C_in, int C_out, i
                          const float* w, const float* bias, int k, int u, int precision,
                          void* stream);
 
+/* ---- speaker encoder -------------------------------------------------------------------------
+ * ECAPA_TDNN.forward(mel_ref, lens=None) -> [B, emb_dim] (indextts/BigVGAN/ECAPA_TDNN.py:543-581, called at
+ * models.py:204) as hand-written fp32 CUDA kernels (csrc/ecapa.cu).  The caller (index_tts_lora_b200/ecapa_native.py)
+ * owns the weight tensors and hands over device pointers in kernel-ready form:
+ *   conv weights   re-laid out as [C_in][k][C_out] fp32 (from the checkpoint's [C_out][C_in][k]);
+ *   BatchNorm      folded to scale = weight / sqrt(running_var + eps), shift = bias - running_mean * scale (eval mode);
+ *   asp_ctx_w      the [att][2 * mfa] slice of asp.tdnn's 1x1 weight that multiplies the broadcast mean | std context;
+ *   asp_tdnn.w     its remaining [mfa][1][att] part.
+ * Pointers must stay valid for the life of the handle.  Same error convention as the plan API. */
+typedef struct bvg_ecapa_tdnn {
+  const float* w;        /* [cin][k][cout] */
+  const float* bias;     /* [cout] */
+  const float* bn_scale; /* [cout] or NULL (plain conv) */
+  const float* bn_shift;
+  int32_t cin, cout, k, dil, relu;
+} bvg_ecapa_tdnn;
+typedef struct bvg_ecapa_block {          /* SERes2NetBlock, ECAPA_TDNN.py:341-426 */
+  bvg_ecapa_tdnn tdnn1, res2[7], tdnn2;
+  const float *se_w1, *se_b1, *se_w2, *se_b2;   /* [se][C], [se], [C][se], [C] */
+} bvg_ecapa_block;
+typedef struct bvg_ecapa_desc {
+  int32_t in_channels, channels, scale, se_channels, att_channels, mfa_channels, emb_dim;
+  bvg_ecapa_tdnn block0;
+  bvg_ecapa_block blocks[3];
+  bvg_ecapa_tdnn mfa, asp_tdnn, asp_conv;
+  const float* asp_ctx_w;                 /* [att][2 * mfa] */
+  const float *asp_bn_scale, *asp_bn_shift;   /* [2 * mfa] */
+  const float *fc_w, *fc_b;               /* [emb][2 * mfa], [emb] */
+} bvg_ecapa_desc;
+typedef struct bvg_ecapa bvg_ecapa;
+int bvg_ecapa_create(const bvg_ecapa_desc* desc, int device, bvg_ecapa** out);
+int bvg_ecapa_destroy(bvg_ecapa* enc);
+/* mel [B, Tm, in_channels] contiguous (F32 / BF16 / F16) on the device -> emb_out fp32 [B, emb_dim]; asynchronous on
+ * `stream`; the ~45 launches are replayed from a CUDA graph per (B, Tm). */
+int bvg_ecapa_forward(bvg_ecapa* enc, const void* mel, int mel_dtype, int B, int Tm, float* emb_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,25 @@ class BvgShardGeom(C.Structure):
                 ("own_left", C.c_int32), ("own_right", C.c_int32), ("own_max", C.c_int32)]
 
 
+class BvgEcapaTdnn(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("bias", C.c_void_p), ("bn_scale", C.c_void_p), ("bn_shift", C.c_void_p),
+                ("cin", C.c_int32), ("cout", C.c_int32), ("k", C.c_int32), ("dil", C.c_int32), ("relu", C.c_int32)]
+
+
+class BvgEcapaBlock(C.Structure):
+    _fields_ = [("tdnn1", BvgEcapaTdnn), ("res2", BvgEcapaTdnn * 7), ("tdnn2", BvgEcapaTdnn),
+                ("se_w1", C.c_void_p), ("se_b1", C.c_void_p), ("se_w2", C.c_void_p), ("se_b2", C.c_void_p)]
+
+
+class BvgEcapaDesc(C.Structure):
+    _fields_ = [("in_channels", C.c_int32), ("channels", C.c_int32), ("scale", C.c_int32), ("se_channels", C.c_int32),
+                ("att_channels", C.c_int32), ("mfa_channels", C.c_int32), ("emb_dim", C.c_int32),
+                ("block0", BvgEcapaTdnn), ("blocks", BvgEcapaBlock * 3),
+                ("mfa", BvgEcapaTdnn), ("asp_tdnn", BvgEcapaTdnn), ("asp_conv", BvgEcapaTdnn),
+                ("asp_ctx_w", C.c_void_p), ("asp_bn_scale", C.c_void_p), ("asp_bn_shift", C.c_void_p),
+                ("fc_w", C.c_void_p), ("fc_b", C.c_void_p)]
+
+
 # every symbol include/bvg.h declares: name -> (restype, argtypes)
 _P, _I, _L = C.c_void_p, C.c_int, C.c_int64
 SYMBOLS = {
@@ -86,6 +105,9 @@ SYMBOLS = {
     "bvg_set_tc_residual_mma": (_I, [_I]),
     "bvg_set_pdl": (_I, [_I]),
     "bvg_set_graphs": (_I, [_I]),
+    "bvg_ecapa_create": (_I, [C.POINTER(BvgEcapaDesc), _I, C.POINTER(_P)]),
+    "bvg_ecapa_destroy": (_I, [_P]),
+    "bvg_ecapa_forward": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "bvg_activation1d": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P]),
     "bvg_amp_layer": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P]),
     "bvg_conv_transpose1d": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _P]),

@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 # shipped library never contains them); _lib.py loads it when BVG_LIB points at it
 EXPERIMENTS = os.environ.get("BVG_EXPERIMENTS") == "1"
 OUT = os.path.join(HERE, "libbvg_exp.so" if EXPERIMENTS else "libbvg.so")
-SOURCES = ["bvg_api.cu", "decode_tc.cu"]
+SOURCES = ["bvg_api.cu", "decode_tc.cu", "ecapa.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
 

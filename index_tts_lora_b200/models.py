@@ -227,6 +227,11 @@ class BigVGAN(nn.Module):
         # replayed from a CUDA graph captured per input shape (same kernels, same numbers).
         self.graph_speaker_encoder = True
         self._spk_graphs = {}
+        # ... and by default it does not go through PyTorch at all on the GPU: csrc/ecapa.cu runs it as five
+        # hand-written fp32 kernels replayed from one CUDA graph (ecapa_native.py).  The PyTorch module above remains the
+        # parameter container (checkpoint keys) and serves CPU tensors, training mode and the `lens` argument.
+        self.native_speaker_encoder = True
+        self._spk_native = None
         self.register_load_state_dict_post_hook(lambda mod, _keys: mod._invalidate())
 
     # ---------------------------------------------------------------- nn.Module plumbing
@@ -234,6 +239,7 @@ class BigVGAN(nn.Module):
         self._weights_dirty = True
         self._spk_cache = None
         self._spk_graphs = {}
+        self._spk_native = None
 
     def _apply(self, fn, *a, **k):       # .to() / .half() / .cuda() change the weights we packed
         self._invalidate()
@@ -343,7 +349,13 @@ class BigVGAN(nn.Module):
             if self._spk_cache is not None and self._spk_cache[0] == key:
                 return self._spk_cache[2]
         emb = None
-        if (self.graph_speaker_encoder and mel_ref.is_cuda and lens is None and not self.training
+        if (self.native_speaker_encoder and mel_ref.is_cuda and lens is None and not self.training
+                and not torch.is_grad_enabled()):
+            from .ecapa_native import NativeSpeakerEncoder
+            if self._spk_native is None or self._spk_native.device != mel_ref.device:
+                self._spk_native = NativeSpeakerEncoder(self.speaker_encoder, mel_ref.device)
+            emb = self._spk_native(mel_ref)
+        elif (self.graph_speaker_encoder and mel_ref.is_cuda and lens is None and not self.training
                 and not torch.is_grad_enabled()):
             emb = self._speaker_encoder_graphed(mel_ref)
         if emb is None:

@@ -284,3 +284,32 @@ def test_graph_replay_and_pdl_are_bit_identical(real):
     for r, a, b in zip(ref, pdl, outs):
         assert torch.equal(r, a), "PDL changed the result"
         assert torch.equal(r, b), "graph replay changed the result"
+
+
+# ----------------------------------------------------------------------------- speaker encoder
+@pytest.mark.parametrize("B,Tm", [(1, 300), (2, 97), (3, 33)])
+def test_native_speaker_encoder_vs_pytorch_fp32(real, B, Tm):
+    """csrc/ecapa.cu (hand-written fp32 kernels, one CUDA graph) against the PyTorch ECAPA_TDNN module on the CPU —
+    itself bit-identical to the reference's (golden spk_emb, tests/test_oracle.py).  fp32 both sides: 1e-5."""
+    from index_tts_lora_b200 import synth
+    m, h = real["m"], real["h"]
+    dev = _dev()
+    mel = synth.synth_mel(B, Tm, h.num_mels, seed=5 + Tm)
+    import copy
+    enc_cpu = copy.deepcopy(m.speaker_encoder).cpu().float().eval()
+    ref = enc_cpu(mel)
+    m.cache_speaker_embedding = False
+    try:
+        for rep in range(2):                        # capture, then replay
+            got = m.speaker_embedding(mel.to(dev)).cpu()
+    finally:
+        m.cache_speaker_embedding = True
+    assert m._spk_native is not None, "the native speaker encoder did not run"
+    assert got.shape == ref.shape == (B, 1, h.speaker_embedding_dim)
+    err = (got - ref).abs().max().item()
+    print(f"native speaker encoder B={B} Tm={Tm}: max-abs {err:.2e} (|emb| max {ref.abs().max().item():.3f})")
+    assert err < 1e-5 * max(1.0, ref.abs().max().item()), err
+    # bf16 mel input (the module under .to(bfloat16) hands the mel over in bf16): same as the fp32 run on the rounded mel
+    got16 = m.speaker_embedding(mel.to(dev).to(torch.bfloat16)).cpu()
+    ref16 = enc_cpu(mel.to(torch.bfloat16).float())
+    assert (got16 - ref16).abs().max().item() < 1e-5 * max(1.0, ref16.abs().max().item())
