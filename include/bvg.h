@@ -233,6 +233,14 @@ int bvg_set_tc_residual_mma(int on);
 int bvg_set_pdl(int on);
 int bvg_set_graphs(int on);
 
+/* bf16 path, wide stages: the activated AMP layers whose output needs 2 or 3 column tiles (C = 384, 768) are launched as
+ * thread-block clusters of that many CTAs.  The CTAs of a cluster convolve the same time tile; each activates every
+ * n-th 32-channel chunk and writes the z tile into the shared-memory ring of ALL of them (st.shared::cluster), so
+ * Activation1d runs once per chunk instead of once per column tile; ring slots are released by multicast
+ * tcgen05.commit.  Same arithmetic per element, bit-identical results.  Process-wide, default on (BVG_CLUSTER=0 at first
+ * use turns it off).  Returns the previous value. */
+int bvg_set_tc_cluster(int on);
+
 /* ---- per-op entry points (tests, and the reference's own native-op boundary) ---------- */
 
 /* Supersedes anti_alias_activation_cuda.forward(input, up_filter, down_filter, alpha, beta)

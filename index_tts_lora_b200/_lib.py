@@ -105,6 +105,7 @@ SYMBOLS = {
     "bvg_set_tc_residual_mma": (_I, [_I]),
     "bvg_set_pdl": (_I, [_I]),
     "bvg_set_graphs": (_I, [_I]),
+    "bvg_set_tc_cluster": (_I, [_I]),
     "bvg_ecapa_create": (_I, [C.POINTER(BvgEcapaDesc), _I, C.POINTER(_P)]),
     "bvg_ecapa_destroy": (_I, [_P]),
     "bvg_ecapa_forward": (_I, [_P, _P, _I, _I, _I, _P, _P]),

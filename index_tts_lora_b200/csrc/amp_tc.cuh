@@ -99,6 +99,8 @@ struct TcArgs {
   int up, pad, cphase;
   const float* a2;             // [Cin padded to 32]  2*exp(alpha)
   const float* nhb;            // [Cin padded to 32]  -0.5/(exp(beta)+1e-9)
+  int cl;                      // thread-block cluster size (= n_tiles, 2 or 3) when the column tiles of a time tile share one
+                               // activation through distributed shared memory; 0 / 1 = every CTA on its own
   long long* trace;            // BVG_EXPERIMENTS builds only: clock-stamped pipeline events of CTA 0 (tools/nar_trace.py)
   float up2[12];               // 2*f[k]  (the x2 gain of resample.py:30 folded in)
   float dn[12];
@@ -200,6 +202,46 @@ __device__ __forceinline__ void umma_commit_e(uint32_t leader, uint32_t bar) {
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// ---- thread-block clusters / distributed shared memory
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {   // my shared address -> the same one in CTA `rank`
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+// remote arrive that also announces `bytes` of bulk-copy traffic for the current phase of that barrier
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t cbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cbar), "r"(bytes) : "memory");
+}
+// bulk copy (async proxy) from my shared memory into a peer CTA's; completes `bytes` on the peer's barrier `cbar`
+__device__ __forceinline__ void dsmem_copy(uint32_t cdst, uint32_t src, uint32_t bytes, uint32_t cbar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(cdst), "r"(src), "r"(bytes), "r"(cbar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cbar) {             // release at cluster scope, remote barrier
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_acq_cluster(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\tWAIT_LOOP_C:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE_C;\n\tbra WAIT_LOOP_C;\n\tDONE_C:\n\t}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// commit that arrives on the barrier at this offset in EVERY CTA of the mask
+__device__ __forceinline__ void umma_commit_mc_e(uint32_t leader, uint32_t bar, uint32_t mask) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t.reg .b16 m;\n\tsetp.ne.b32 e, %1, 0;\n\tcvt.u16.u32 m, %2;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}\n"
+      ::"r"(bar), "r"(leader), "r"(mask) : "memory");
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -383,6 +425,16 @@ __device__ __noinline__ void act_run_edge(const uint32_t* xk, uint32_t* zk, int 
 // Four warps (q = TMEM lane quarter, etid = 0..127): TMEM -> (+bias, +cond, +resid, +sum, /div) -> bf16 -> HBM; they walk
 // the same static tile sequence as the other roles.  (The generic first-generation epilogue that also did the
 // ConvTranspose1d scatter was retired in favour of epilogue_pipe / epilogue_up below; epilogue_fir serves amp_fir.cuh.)
+// The static tile sequence of a CTA: w = w0, w0 + wstep, ...  (w = time tile * n_tiles + column tile).  Plain launch: CTA i
+// starts at tile i and strides by the grid.  Cluster launch (a.cl = n_tiles CTAs per cluster): the CTAs of a cluster take the
+// n_tiles column tiles of the SAME time tile, cluster j starts at time tile j and strides by the number of clusters.
+__device__ __forceinline__ int tile_w0(const TcArgs& a) {
+  return a.cl > 1 ? (int)(blockIdx.x / a.cl) * a.n_tiles + (int)(blockIdx.x % a.cl) : (int)blockIdx.x;
+}
+__device__ __forceinline__ int tile_wstep(const TcArgs& a) {
+  return a.cl > 1 ? (int)(gridDim.x / a.cl) * a.n_tiles : (int)gridDim.x;
+}
+
 struct TileCursor {            // monotone walk over the per-utterance tile prefix table
   const int* prefix;
   int b = 0;
@@ -495,7 +547,7 @@ __device__ __forceinline__ void epilogue_fir_t(const TcArgs& a, float* bias_s, c
   const u64 rdiv2 = pk(rdiv, rdiv);
   TileCursor cur{prefix};
   int it = 0, last_b = -1, last_nt = -1;
-  for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++it) {
+  for (int w = tile_w0(a); w < total_tiles; w += tile_wstep(a), ++it) {
     int b, t0, nt;
     cur.locate(w, n_tiles, b, t0, nt);
     const int T = a.lengths ? a.lengths[b] * a.rate : a.Tmax;
@@ -686,8 +738,8 @@ __device__ __forceinline__ void epilogue_pipe_t(const TcArgs& a, float* bias_s, 
     c2.locate(w, n_tiles, b, t0, nt);
     T_next = a.lengths ? __ldg(a.lengths + b) * a.rate : a.Tmax;
   };
-  prefetch_tile(blockIdx.x);
-  for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++it) {
+  prefetch_tile(tile_w0(a));
+  for (int w = tile_w0(a); w < total_tiles; w += tile_wstep(a), ++it) {
     int b, t0, nt;
     cur.locate(w, n_tiles, b, t0, nt);
     const int T = T_next;
@@ -741,7 +793,7 @@ __device__ __forceinline__ void epilogue_pipe_t(const TcArgs& a, float* bias_s, 
     };
 #pragma unroll 1
     for (int s = 0; s < LA; ++s) issue(s);
-    prefetch_tile(w + gridDim.x);
+    prefetch_tile(w + tile_wstep(a));
     if (q == 0) mbar_wait_relaxed(bar_accfull0 + 8 * as, ause & 1, a.Cin <= 96 ? 600u : 120u);
     asm volatile("bar.sync 2, 128;" ::: "memory");
     tc_fence_after();
@@ -820,12 +872,12 @@ __device__ __forceinline__ void epilogue_up(const TcArgs& a, float* bias_s, cons
     c2.locate(w, n_tiles, b, t0, nt);
     Tin_next = __ldg(a.lengths + b) * a.rate;
   };
-  ahead(blockIdx.x);
-  for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++it) {
+  ahead(tile_w0(a));
+  for (int w = tile_w0(a); w < total_tiles; w += tile_wstep(a), ++it) {
     int b, t0, nt;
     cur.locate(w, n_tiles, b, t0, nt);
     const int Tin = Tin_next;
-    ahead(w + gridDim.x);
+    ahead(w + tile_wstep(a));
     const int T = Tin + extra, Tout = Tin * a.up;
     const int as = (nacc == 2) ? (it & 1) : 0;
     const int ause = (nacc == 2) ? (it >> 1) : it;
@@ -974,7 +1026,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
   if (warp == NW_ACT && lane == 0) {
     // two MMA issuer warps (one per M block): every "the MMAs that read this are done" barrier takes two commits
     for (int i = 0; i < NX_MAX; ++i) { mbar_init(BAR_XFULL(i), 1); mbar_init(BAR_XEMPTY(i), ACT ? NW_ACT : 2); }
-    for (int i = 0; i < NZ_MAX; ++i) { mbar_init(BAR_ZFULL(i), NW_ACT); mbar_init(BAR_ZEMPTY(i), 2); }
+    for (int i = 0; i < NZ_MAX; ++i) { mbar_init(BAR_ZFULL(i), NW_ACT); mbar_init(BAR_ZEMPTY(i), 2 * ((ACT && a.cl > 1) ? a.cl : 1)); }
     for (int i = 0; i < 2; ++i) { mbar_init(BAR_ACCFULL(i), 2); mbar_init(BAR_ACCEMPTY(i), 4); }
     for (int i = 0; i < R_RING; ++i) { mbar_init(BAR_RFULL(i), 1); mbar_init(BAR_REMPTY(i), 2); }
     for (int i = 0; i < W_STAGES_MAX; ++i) { mbar_init(BAR_WFULL(i), 1); mbar_init(BAR_WEMPTY(i), 2); }
@@ -991,6 +1043,13 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int total_tiles = prefix[a.B] * n_tiles;
+  // cluster mode: the n_tiles column tiles of a time tile run in one cluster; chunk c of the tile is activated by the CTA
+  // of rank c % ncl, which writes the z tile into every CTA's ring (distributed shared memory) and arrives on every
+  // CTA's "z full" barrier; "z empty" takes a multicast commit from every CTA's MMA issuers
+  const int ncl = (ACT && a.cl > 1) ? a.cl : 1;
+  const uint32_t crank = ncl > 1 ? cluster_ctarank() : 0u;
+  const int w0 = tile_w0(a), wstep = tile_wstep(a);
+  if (ncl > 1) cluster_sync_all();     // every CTA's barriers are initialised before anyone arrives remotely
   pdl_wait();          // the prologue above only read launch constants (lengths, parameters); activations from here on
 
   if (warp < NW_ACT) {
@@ -1019,6 +1078,11 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
       // Channel groups past C_in (C = 24: group 3; C = 48: groups 2-3 of the second chunk) carry zero weights: their
       // warps skip the arithmetic.  Their z rows are zeroed once so that no stale NaN pattern reaches the MMA.
       const int live_groups = a.Cin >> 3;
+      uint32_t peer_base[2] = {0u, 0u};           // shared-window base of the other CTAs of my cluster
+      if (ncl > 1) {
+        peer_base[0] = mapa_u32(s_base, (crank + 1) % ncl);
+        if (ncl > 2) peer_base[1] = mapa_u32(s_base, (crank + 2) % ncl);
+      }
       if ((NCH - 1) * 4 + kg >= live_groups) {
         for (int s = 0; s < NZ; ++s) {
           uint32_t* zk = reinterpret_cast<uint32_t*>(smem + OFF_Z + s * Z_BUF_BYTES) + kg * (ZR * 4) + p;
@@ -1033,16 +1097,16 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
       TileCursor cur{prefix};
       int xb = 0, xph = 0, zb = 0, zph = 0;     // ring slot / phase of the next chunk
       int b = 0, t0 = 0, nt = 0, T = 0;
-      if ((int)blockIdx.x < total_tiles) {
-        cur.locate(blockIdx.x, n_tiles, b, t0, nt);
+      if (w0 < total_tiles) {
+        cur.locate(w0, n_tiles, b, t0, nt);
         T = a.lengths ? __ldg(a.lengths + b) * a.rate : a.Tmax;
       }
-      float2 a2n = __ldg(reinterpret_cast<const float2*>(a.a2 + kg * 8 + 2 * p));
-      float2 nhbn = __ldg(reinterpret_cast<const float2*>(a.nhb + kg * 8 + 2 * p));
-      for (int w = blockIdx.x; w < total_tiles; w += gridDim.x) {
+      float2 a2n = __ldg(reinterpret_cast<const float2*>(a.a2 + (int)crank * KC + kg * 8 + 2 * p));     // my first chunk
+      float2 nhbn = __ldg(reinterpret_cast<const float2*>(a.nhb + (int)crank * KC + kg * 8 + 2 * p));
+      for (int w = w0; w < total_tiles; w += wstep) {
         int b2 = 0, t02 = 0, nt2 = 0, T2 = 0;
-        if (w + (int)gridDim.x < total_tiles) {
-          cur.locate(w + gridDim.x, n_tiles, b2, t02, nt2);
+        if (w + wstep < total_tiles) {
+          cur.locate(w + wstep, n_tiles, b2, t02, nt2);
           T2 = a.lengths ? __ldg(a.lengths + b2) * a.rate : a.Tmax;
         }
         const int m0 = t0 - hc + rowS;
@@ -1051,11 +1115,16 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
         // because the run takes part in shuffles)
         const bool edge = __any_sync(0xffffffffu, (m0 - 3 < 0) || (m0 + L + 2 > T - 1));
         for (int c = 0; c < NCH; ++c) {
+          if (ncl > 1 && (uint32_t)(c % ncl) != crank) {      // a peer activates this chunk and fills my z slot
+            if (++zb == NZ) { zb = 0; zph ^= 1; }
+            continue;
+          }
           k.a2 = pk(a2n.x, a2n.y);
           k.nhb = pk(nhbn.x, nhbn.y);
           k.hb = pk(-nhbn.x, -nhbn.y);
-          if (NCH > 1) {
-            const int chn = (c + 1 == NCH ? 0 : c + 1) * KC + kg * 8 + 2 * p;
+          if (NCH > 1) {                                        // parameters of my NEXT chunk (ncl apart in cluster mode)
+            const int cn = (c + ncl >= NCH) ? (int)crank : c + ncl;
+            const int chn = cn * KC + kg * 8 + 2 * p;
             a2n = __ldg(reinterpret_cast<const float2*>(a.a2 + chn));
             nhbn = __ldg(reinterpret_cast<const float2*>(a.nhb + chn));
           }
@@ -1084,10 +1153,28 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
               act_run<L, false>(xk, zk, rowS, smask, m0, xlo, T, k, lane);
             }
           }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // z stores -> async proxy (UMMA)
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // z stores -> async proxy (UMMA, bulk copies)
           __syncwarp();
           if (lane == 0) {
             mbar_arrive(BAR_ZFULL(zb));
+            if (ncl > 1) {
+              // my rows [vlo, vhi) of channel group kg go to the same place in every peer's ring as one bulk copy through
+              // the async proxy, which completes its bytes on the peer's "z full" barrier: data and signal travel together
+              // (remote generic-proxy stores followed by a remote arrive were NOT ordered before the peer's UMMA reads)
+              const uint32_t bytes = live ? (uint32_t)(vhi - vlo) * 16u : 0u;
+              const uint32_t off = (uint32_t)(OFF_Z + zb * Z_BUF_BYTES + (kg * ZR + vlo) * 16);
+              const uint32_t boff = BAR_ZFULL(zb) - s_base;
+#pragma unroll
+              for (int j = 0; j < 2; ++j)
+                if (j < ncl - 1) {
+                  if (bytes) {
+                    mbar_arrive_expect_tx_cluster(peer_base[j] + boff, bytes);
+                    dsmem_copy(peer_base[j] + off, s_base + off, bytes, peer_base[j] + boff);
+                  } else {
+                    mbar_arrive_cluster(peer_base[j] + boff);
+                  }
+                }
+            }
             mbar_arrive(BAR_XEMPTY(xb));
           }
           if (++xb == NX) { xb = 0; xph ^= 1; }
@@ -1103,10 +1190,11 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
       if (lane == 0) {
         TileCursor cur{prefix};
         int xb = 0, xph = 0;
-        for (int w = blockIdx.x; w < total_tiles; w += gridDim.x) {
+        for (int w = w0; w < total_tiles; w += wstep) {
           int b, t0, nt;
           cur.locate(w, n_tiles, b, t0, nt);
           for (int c = 0; c < NCH; ++c) {
+            if (ncl > 1 && (uint32_t)(c % ncl) != crank) continue;    // that chunk is activated by a peer CTA
             mbar_wait_relaxed(BAR_XEMPTY(xb), xph ^ 1, 400);
             // activated layers never read the channel groups past C_in (their warps skip); plain convs feed the
             // x tile to the MMA as it is and need the TMA zero fill of those groups
@@ -1131,7 +1219,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
       if (lane == 0) {
         int stage = 0, phase = 0, rs = 0, rph = 0;
         TileCursor cur{prefix};
-        for (int w = blockIdx.x; w < total_tiles; w += gridDim.x) {
+        for (int w = w0; w < total_tiles; w += wstep) {
           int b, t0, nt;
           cur.locate(w, n_tiles, b, t0, nt);
           const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wt) + (size_t)nt * NCH * a.K * tile_bytes;
@@ -1190,13 +1278,17 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
         const u64 hiA = make_sdesc(0, lboA, 128), hiB = make_sdesc(0, lboB, 128);
         const uint32_t ksA = 2 * lboA / 16, ksB = 2 * lboB / 16, tileU = (uint32_t)tile_bytes / 16;
         const int ND = ACT ? NZ : NX;                       // depth of the A-operand ring (z tiles, or raw x tiles)
-        const uint32_t ring0 = (ACT ? (s_base + OFF_Z) : (s_base + OFF_X + (X_LEAD - a.lead) * 16)) >> 4;
+        // Under a cluster launch the shared::cta window address of CTA rank r carries r in its upper bits: only the low
+        // 18 bits (offset inside this SM's shared memory) belong in a UMMA descriptor's 14-bit address field — unmasked,
+        // the rank bit landed in the leading-byte-offset field of every CTA but rank 0.
+        const uint32_t s_loc = s_base & 0x3FFFFu;
+        const uint32_t ring0 = (ACT ? (s_loc + OFF_Z) : (s_loc + OFF_X + (X_LEAD - a.lead) * 16)) >> 4;
         const uint32_t ringU = (ACT ? Z_BUF_BYTES : X_BUF_BYTES) >> 4;
         const uint32_t barF = ACT ? BAR_ZFULL(0) : BAR_XFULL(0), barE = ACT ? BAR_ZEMPTY(0) : BAR_XEMPTY(0);
         const bool lazy = ACT && a.Cin <= 96 && !BVG_DBGBIT(a, 4);
         const u64 hiR = make_sdesc(0, M_TILE * 16, 128);    // residual slot: 256 rows per 8-channel group
         int stage = 0, phase = 0, rb = 0, rph = 0, it = 0, rr = 0, rrph = 0;
-        for (int w = blockIdx.x; w < total_tiles; w += gridDim.x, ++it) {
+        for (int w = tile_w0(a); w < total_tiles; w += tile_wstep(a), ++it) {
           const int as = (nacc == 2) ? (it & 1) : 0;
           mbar_wait(BAR_ACCEMPTY(as), ((((nacc == 2) ? (it >> 1) : it) & 1) ^ 1));   // epilogue has drained this stage
           tc_fence_after();
@@ -1204,7 +1296,8 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
           uint32_t accflag = 0;
           for (int c = 0; c < NCH; ++c) {
             // narrow layers are bound by the activation warps' issue slots: the issuer sleeps between polls there
-            if (lazy) mbar_wait_relaxed(barF + 8 * rb, rph, 300);
+            if (ncl > 1) mbar_wait_acq_cluster(barF + 8 * rb, rph);     // arrivals (and bulk-copy bytes) come from peer CTAs too
+            else if (lazy) mbar_wait_relaxed(barF + 8 * rb, rph, 300);
             else mbar_wait(barF + 8 * rb, rph);
             tc_fence_after();
             const uint32_t aU = ring0 + (uint32_t)rb * ringU;
@@ -1212,7 +1305,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
               const int taps = min(tps, a.K - s * tps);
               mbar_wait(BAR_WFULL(stage), phase);
               tc_fence_after();
-              const uint32_t wU = (s_base + OFF_W + stage * W_STAGE_BYTES) >> 4;
+              const uint32_t wU = (s_loc + OFF_W + stage * W_STAGE_BYTES) >> 4;
               for (int tj = 0; tj < taps; ++tj) {
                 const uint32_t a0 = aU + (uint32_t)((s * tps + tj) * a.dil) + mbk * 128u;
                 const uint32_t b0 = wU + (uint32_t)tj * tileU;
@@ -1223,7 +1316,8 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
               umma_commit_e(leader, BAR_WEMPTY(stage));          // weight stage free once these MMAs retire
               if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
             }
-            umma_commit_e(leader, barE + 8 * rb);
+            if (ncl > 1 && !BVG_DBGBIT(a, 4096)) umma_commit_mc_e(leader, barE + 8 * rb, (1u << ncl) - 1u);   // frees the slot in every CTA's ring
+            else umma_commit_e(leader, barE + 8 * rb);
             if (++rb == ND) { rb = 0; rph ^= 1; }
             // + residual (+ running sum) chunk c: D += R x I, two K steps of 16 channels
             if (RM && c < a.nchr)
@@ -1231,8 +1325,8 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
                 mbar_wait(BAR_RFULL(rr), rrph);
                 mbar_wait(BAR_WFULL(stage), phase);
                 tc_fence_after();
-                const uint32_t r0 = (s_base + OFF_R + rr * R_SLOT_BYTES) >> 4;
-                const uint32_t b0 = (s_base + OFF_W + stage * W_STAGE_BYTES) >> 4;
+                const uint32_t r0 = (s_loc + OFF_R + rr * R_SLOT_BYTES) >> 4;
+                const uint32_t b0 = (s_loc + OFF_W + stage * W_STAGE_BYTES) >> 4;
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks)
                   umma_bf16_e(leader, tm, hiR | (r0 + ks * (2 * M_TILE) + mbk * 128u), hiB | (b0 + ks * ksB), idesc, 1u);
@@ -1262,6 +1356,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
   }
   tc_fence_before();
   __syncthreads();
+  if (ncl > 1) cluster_sync_all();     // nobody leaves while a peer may still store into its rings or arrive on its barriers
   if (warp == NW_ACT + 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
   }

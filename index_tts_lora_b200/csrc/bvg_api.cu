@@ -759,6 +759,7 @@ int bvg_set_tc_narrow_max_channels(int max_c) { return bvg::tc_set_nar_max_c(max
 int bvg_set_tc_split_min_channels(int min_c) { return bvg::tc_set_split_min_c(min_c); }
 int bvg_set_tc_residual_mma(int on) { return bvg::tc_set_residual_mma(on); }
 int bvg_set_graphs(int on) { return bvg::tc_set_graphs(on); }
+int bvg_set_tc_cluster(int on) { return bvg::tc_set_cluster(on); }
 int bvg_set_pdl(int on) { return bvg::set_pdl(on); }
 
 int bvg_plan_read_profile(bvg_plan* p, bvg_profile* out) {

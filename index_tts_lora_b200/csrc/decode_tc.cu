@@ -440,7 +440,7 @@ static int launch_inst_rm(const CUtensorMap& map, const CUtensorMap& mapr, const
   // roles (local memory) and the few global scalars: ask for the smallest carve-out that holds this launch.
   const int want = std::min(100, (smem + 1024) * 100 / (228 * 1024) + 1);
   BVG_CUDA(func_attr_once((const void*)kern, cudaFuncAttributePreferredSharedMemoryCarveout, want));
-  BVG_CUDA(launch_k(kern, grid, dim3(NTHREADS), (size_t)smem, st, true, map, mapr, mapq, a));
+  BVG_CUDA(launch_kc(kern, grid, dim3(NTHREADS), (size_t)smem, st, true, a.cl, map, mapr, mapq, a));
   return 0;
 }
 
@@ -528,6 +528,21 @@ static int split_min_c() {
   return g_split_min_c;
 }
 static bool split_layer(int Cin) { return split_min_c() > 0 && Cin >= split_min_c(); }
+
+// Thread-block clusters for the multi-column-tile activated layers (see launch_tc); default on.
+static std::atomic<int> g_cluster{-1};
+int tc_set_cluster(int on) {
+  const int cur = g_cluster.load(), old = cur < 0 ? 1 : cur;
+  g_cluster = on ? 1 : 0;
+  return old;
+}
+static bool cluster_on() {
+  if (g_cluster < 0) {
+    const char* e = getenv("BVG_CLUSTER");
+    g_cluster = (!e || atoi(e) != 0) ? 1 : 0;
+  }
+  return g_cluster != 0;
+}
 
 // Residual / running-sum add by identity MMAs (amp_tc.cuh) on the layers where it pays; off = always in the epilogue.
 static std::atomic<int> g_rmma{-1};
@@ -645,8 +660,19 @@ static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, cons
     const long long Tb = (q.h_len ? (long long)q.h_len[b] * q.rate : q.Tstride) + extra;
     tiles += (Tb + M_TILE - 1) / M_TILE;
   }
+  const long long time_tiles = tiles;
   tiles *= L.n_tiles;
   dim3 grid((unsigned)std::min<long long>(tiles, q.sm_count > 0 ? q.sm_count : 148));
+  // Cluster mode for the activated layers with 2 or 3 column tiles (C = 384, 768): the column tiles of a time tile form
+  // one thread-block cluster and share ONE activation of every 32-channel chunk through distributed shared memory instead
+  // of recomputing it per column tile (amp_tc.cuh).  Same arithmetic, same results.
+  a.cl = 0;
+  if (aw && !q.up && cluster_on() && (L.n_tiles == 2 || L.n_tiles == 3) && cw.Cin % KC == 0) {
+    const long long sms = q.sm_count > 0 ? q.sm_count : 148;
+    const long long ncl = std::min<long long>(time_tiles, sms / L.n_tiles);
+    a.cl = L.n_tiles;
+    grid = dim3((unsigned)(ncl * L.n_tiles));
+  }
   const double samples = (p ? p->cur_sum_frames : 0.0) * q.rate;
   prof_begin(p, st, q.cls, 2.0 * cw.Cin * cw.Cout * cw.K * samples,
              samples * 2.0 * (cw.Cin + cw.Cout + (q.resid ? cw.Cout : 0) + (q.acc_in ? cw.Cout : 0)) +

@@ -20,6 +20,7 @@ int tc_set_nar_max_c(int v);
 int tc_set_split_min_c(int v);
 int tc_set_residual_mma(int on);
 int tc_set_graphs(int on);
+int tc_set_cluster(int on);
 int set_pdl(int on);
 // time-split P2P decode (decode_tc.cu)
 int tc_shard_setup(bvg_plan* p, const bvg_shard_geom* g, cudaStream_t st);

@@ -649,3 +649,71 @@ def test_ragged_batch_bf16_residual_mma_vs_epilogue_add():
         assert snr > 40.0, (b, L, snr)
         if L < max(lengths):
             assert y_mma[b, :, L * 1024:].abs().max().item() == 0.0
+
+
+# ============================================================================= thread-block clusters on the wide layers
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,d", [(3, 1), (7, 3), (11, 5)])
+@pytest.mark.parametrize("C,T", [(384, 257), (384, 1500), (768, 70), (768, 700)])
+@pytest.mark.parametrize("with_resid", [False, True])
+def test_amp_layer_bf16_cluster_equals_plain(k, d, C, T, with_resid):
+    """Wide activated layers (2 / 3 column tiles) launched as thread-block clusters that share ONE Activation1d per
+    32-channel chunk through distributed shared memory (bvg_set_tc_cluster) against the plain launch that recomputes it
+    per column tile: the same arithmetic per element, so the results must be bit-identical — and within the per-layer
+    bar of the fp32 oracle."""
+    from index_tts_lora_b200.models import AMPBlock1
+    from index_tts_lora_b200.ops import amp_layer
+    from index_tts_lora_b200 import synth, _lib
+    from index_tts_lora_b200.config import AttrDict
+    O = _oracle()
+    dev = _dev()
+    lib = _lib.load()
+    blk = AMPBlock1(AttrDict(snake_logscale=True), C, k, (d, d, d), activation="snakebeta")
+    sd = synth.synth_state_dict(blk.state_dict(), seed=k * 100 + d, profile="stress")
+    blk.load_state_dict(sd)
+    x = torch.randn(2, C, T, generator=synth._gen(1, f"x{C}{T}"))
+    r = torch.randn(2, C, T, generator=synth._gen(2, f"r{C}{T}")) if with_resid else None
+    old = lib.bvg_set_tc_cluster(0)
+    try:
+        y0 = amp_layer(x.to(dev), blk.convs1[0], blk.activations[0], resid=None if r is None else r.to(dev), precision="bf16").cpu()
+        lib.bvg_set_tc_cluster(1)
+        y1 = amp_layer(x.to(dev), blk.convs1[0], blk.activations[0], resid=None if r is None else r.to(dev), precision="bf16").cpu()
+    finally:
+        lib.bvg_set_tc_cluster(old)
+    assert torch.equal(y0, y1), (y0.float() - y1.float()).abs().max().item()
+    if T <= 300:
+        ref = O.amp_layer(x, sd, "activations.0", "convs1.0", k, d)
+        if r is not None:
+            ref = ref + r
+        assert _snr(ref, y1) > 35.0, _snr(ref, y1)
+
+
+@pytest.mark.gpu
+def test_ragged_batch_bf16_cluster_equals_plain():
+    """Mixed-length batch at the real config, cluster launches against plain launches: bit-identical waveforms, zero
+    tails — tiles past an utterance's end, the ragged tile-prefix table and the cluster tile walk agree."""
+    from index_tts_lora_b200.config import default_config
+    from index_tts_lora_b200 import synth, _lib
+    from index_tts_lora_b200.models import BigVGAN
+    dev = _dev()
+    lib = _lib.load()
+    h = default_config()
+    m = BigVGAN(h)
+    m.load_state_dict(synth.synth_state_dict(m.state_dict(), seed=1234, profile="init"))
+    m = m.to(dev).eval()
+    m.precision = "bf16"
+    lengths = [67, 7, 1, 130, 33]
+    lat = synth.synth_latent(len(lengths), max(lengths), h.gpt_dim, seed=3).to(dev)
+    emb = m.speaker_embedding(synth.synth_mel(1, 120, h.num_mels, seed=4).to(dev)).expand(len(lengths), -1, -1)
+    old = lib.bvg_set_tc_cluster(0)
+    try:
+        y0 = m.decode(lat, emb, lengths=lengths, out_dtype=torch.float32).cpu()
+        lib.bvg_set_tc_cluster(1)
+        y1 = m.decode(lat, emb, lengths=lengths, out_dtype=torch.float32).cpu()
+    finally:
+        lib.bvg_set_tc_cluster(old)
+    assert torch.isfinite(y1).all()
+    assert torch.equal(y0, y1), (y0 - y1).abs().max().item()
+    for b, L in enumerate(lengths):
+        if L < max(lengths):
+            assert y1[b, :, L * 1024:].abs().max().item() == 0.0
