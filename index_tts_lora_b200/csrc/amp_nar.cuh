@@ -91,18 +91,7 @@ template <int NUB> struct Sched;
 template <> struct Sched<10> { static constexpr uint32_t ZMASK = (1u << 2) | (1u << 5) | (1u << 7) | (1u << 11) | (1u << 14); };
 template <> struct Sched<11> { static constexpr uint32_t ZMASK = (1u << 1) | (1u << 4) | (1u << 7) | (1u << 11) | (1u << 14); };
 
-// pipeline trace (experiments builds): record (code, clock) for the first tiles of CTA 0; one writer per slot
-#ifdef BVG_EXPERIMENTS
-#define NAR_TRACE(a, slot, code)                                                                       \
-  do {                                                                                                 \
-    if ((a).trace && blockIdx.x == 0 && (slot) < 4096 && (threadIdx.x & 31) == 0) {                    \
-      (a).trace[2 * (slot)] = (long long)(code);                                                       \
-      (a).trace[2 * (slot) + 1] = clock64();                                                           \
-    }                                                                                                  \
-  } while (0)
-#else
-#define NAR_TRACE(a, slot, code) do { } while (0)
-#endif
+#define NAR_TRACE(a, slot, code) TC_TRACE(a, slot, code)
 
 template <int NUB, bool RM>
 __global__ void __launch_bounds__(NTHREADS_N, 1)

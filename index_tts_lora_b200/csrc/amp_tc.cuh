@@ -242,6 +242,19 @@ __device__ __forceinline__ void umma_commit_mc_e(uint32_t leader, uint32_t bar, 
       ::"r"(bar), "r"(leader), "r"(mask) : "memory");
 }
 
+// pipeline trace (experiments builds): record (code, clock) for the first tiles of CTA 0; one writer per slot
+#ifdef BVG_EXPERIMENTS
+#define TC_TRACE(a, slot, code)                                                                        \
+  do {                                                                                                 \
+    if ((a).trace && blockIdx.x == 0 && (slot) < 4096 && (threadIdx.x & 31) == 0) {                    \
+      (a).trace[2 * (slot)] = (long long)(code);                                                       \
+      (a).trace[2 * (slot) + 1] = clock64();                                                           \
+    }                                                                                                  \
+  } while (0)
+#else
+#define TC_TRACE(a, slot, code) do { } while (0)
+#endif
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -611,6 +624,7 @@ __device__ __forceinline__ void epilogue_fir_t(const TcArgs& a, float* bias_s, c
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_accempty0 + 8 * as);
+    if (q == 0) TC_TRACE(a, 3300 + it, 6);
     // un-activated consumers (ConvTranspose1d) read one row past the end: keep rows [T, T+8) zero
     // when the utterance ends exactly on this tile's boundary (otherwise they were zeroed above)
     if (T == t0 + M_TILE && T < a.Tmax && T < a.st_hi && q == 0) {
@@ -797,6 +811,7 @@ __device__ __forceinline__ void epilogue_pipe_t(const TcArgs& a, float* bias_s, 
     if (q == 0) mbar_wait_relaxed(bar_accfull0 + 8 * as, ause & 1, a.Cin <= 96 ? 600u : 120u);
     asm volatile("bar.sync 2, 128;" ::: "memory");
     tc_fence_after();
+    if (q == 0) TC_TRACE(a, 3200 + it, 5);
     const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * n_tile);
 #pragma unroll 1
     for (int s = 0; s < nst; ++s) {
@@ -820,6 +835,7 @@ __device__ __forceinline__ void epilogue_pipe_t(const TcArgs& a, float* bias_s, 
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_accempty0 + 8 * as);
+    if (q == 0) TC_TRACE(a, 3300 + it, 6);
     // un-activated consumers (ConvTranspose1d) read one row past the end: keep rows [T, T+8) zero
     // when the utterance ends exactly on this tile's boundary (otherwise they were zeroed above)
     if (T == t0 + M_TILE && T < a.Tmax && T < a.st_hi && q == 0) {
@@ -1051,6 +1067,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
   const int w0 = tile_w0(a), wstep = tile_wstep(a);
   if (ncl > 1) cluster_sync_all();     // every CTA's barriers are initialised before anyone arrives remotely
   pdl_wait();          // the prologue above only read launch constants (lengths, parameters); activations from here on
+  if (warp == 0) TC_TRACE(a, 1, 9);
 
   if (warp < NW_ACT) {
     // ===================== activation warps =====================
@@ -1097,6 +1114,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
       TileCursor cur{prefix};
       int xb = 0, xph = 0, zb = 0, zph = 0;     // ring slot / phase of the next chunk
       int b = 0, t0 = 0, nt = 0, T = 0;
+      [[maybe_unused]] int trc = 0;
       if (w0 < total_tiles) {
         cur.locate(w0, n_tiles, b, t0, nt);
         T = a.lengths ? __ldg(a.lengths + b) * a.rate : a.Tmax;
@@ -1134,11 +1152,18 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
           const bool live = vlo < ZW && c * 4 + kg < live_groups;
           if (live) {
             mbar_wait(BAR_XFULL(xb), xph);
+            if (warp == 0 && trc < 480) TC_TRACE(a, 2000 + trc, 8);
             mbar_wait(BAR_ZEMPTY(zb), zph ^ 1);
           } else {
-            mbar_wait_relaxed(BAR_XFULL(xb), xph, 1000);
-            mbar_wait_relaxed(BAR_ZEMPTY(zb), zph ^ 1, 1000);
+            // Nothing to read or write: this warp only owes the two barriers its arrival, and it pays EARLY — as soon as
+            // the previous phase of each barrier is complete (so that the arrival counts for this chunk's phase), long
+            // before the live warps finish the chunk.  (It used to wait for the x tile and the z slot like a live warp,
+            // asleep between polls: every hand-over of a C = 24 / 48 layer then waited for the sleepiest idle warp — the
+            // MMA issuer got a chunk 5-9 kcycles after the live warps had finished it, pipeline trace, round 2.)
+            mbar_wait_relaxed(BAR_ZFULL(zb), zph ^ 1, 500);
+            mbar_wait_relaxed(BAR_XEMPTY(xb), xph ^ 1, 500);
           }
+          if (warp == 0 && trc < 480) TC_TRACE(a, 600 + trc, 7);
           if (live) {
             const uint32_t* xk = reinterpret_cast<const uint32_t*>(smem + OFF_X + xb * X_BUF_BYTES) + kg * (XRA * 4) + p;
             uint32_t* zk = reinterpret_cast<uint32_t*>(smem + OFF_Z + zb * Z_BUF_BYTES) + kg * (ZR * 4) + p;
@@ -1177,6 +1202,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
             }
             mbar_arrive(BAR_XEMPTY(xb));
           }
+          if (warp == 0) { if (trc < 480) TC_TRACE(a, 100 + trc, 1); ++trc; }
           if (++xb == NX) { xb = 0; xph ^= 1; }
           if (++zb == NZ) { zb = 0; zph ^= 1; }
         }
@@ -1190,23 +1216,36 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
       if (lane == 0) {
         TileCursor cur{prefix};
         int xb = 0, xph = 0;
+        [[maybe_unused]] int trx = 0;
         for (int w = w0; w < total_tiles; w += wstep) {
           int b, t0, nt;
           cur.locate(w, n_tiles, b, t0, nt);
           for (int c = 0; c < NCH; ++c) {
             if (ncl > 1 && (uint32_t)(c % ncl) != crank) continue;    // that chunk is activated by a peer CTA
-            mbar_wait_relaxed(BAR_XEMPTY(xb), xph ^ 1, 400);
+            mbar_wait_relaxed(BAR_XEMPTY(xb), xph ^ 1, 150);
+            if (trx < 480) TC_TRACE(a, 2500 + trx, 11);
+            ++trx;
             // activated layers never read the channel groups past C_in (their warps skip); plain convs feed the
             // x tile to the MMA as it is and need the TMA zero fill of those groups
             const int lg = ACT ? min(4, (a.Cin >> 3) - c * 4) : 4;
             mbar_expect_tx(BAR_XFULL(xb), (uint32_t)lg * (X_TX_BYTES / 4));
             const uint32_t dst = s_base + OFF_X + xb * X_BUF_BYTES;
+            // The XR rows of one (utterance, channel group) are contiguous in the blocked layout: a tile whose window lies
+            // inside the buffer takes one 1-D bulk copy per group (5 KB) instead of two tensor boxes, which the TMA unit
+            // walks 16-byte row by row (~1 row / clk).  Windows that leave [0, Tmax) keep the tensor path for its zero fill.
+            if (ACT && a.xin && t0 - X_LEAD >= 0 && t0 - X_LEAD + XR <= a.Tmax) {
+              const __nv_bfloat16* src = a.xin + (((size_t)b * a.xgroups + c * 4) * a.Tmax + (t0 - X_LEAD)) * 8;
 #pragma unroll
-            for (int kg = 0; kg < 4; ++kg)
+              for (int kg = 0; kg < 4; ++kg)
+                if (kg < lg) bulk_load(dst + kg * (XRA * 16), src + (size_t)kg * a.Tmax * 8, XR * 16, BAR_XFULL(xb));
+            } else {
 #pragma unroll
-              for (int h = 0; h < 2; ++h)
-                if (kg < lg) tma_load_4d(dst + kg * (XRA * 16) + h * (BOXR * 16), &tmx, 0, t0 - X_LEAD + h * BOXR, c * 4 + kg, b,
-                            BAR_XFULL(xb));
+              for (int kg = 0; kg < 4; ++kg)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                  if (kg < lg) tma_load_4d(dst + kg * (XRA * 16) + h * (BOXR * 16), &tmx, 0, t0 - X_LEAD + h * BOXR, c * 4 + kg, b,
+                              BAR_XFULL(xb));
+            }
             if (++xb == NX) { xb = 0; xph ^= 1; }
           }
         }
@@ -1294,12 +1333,14 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
           tc_fence_after();
           const uint32_t tm = tmem + (uint32_t)(as * 2 * n_tile) + mbk * (uint32_t)n_tile;
           uint32_t accflag = 0;
+          if (mbk == 0) TC_TRACE(a, 3000 + it, 3);
           for (int c = 0; c < NCH; ++c) {
             // narrow layers are bound by the activation warps' issue slots: the issuer sleeps between polls there
             if (ncl > 1) mbar_wait_acq_cluster(barF + 8 * rb, rph);     // arrivals (and bulk-copy bytes) come from peer CTAs too
             else if (lazy) mbar_wait_relaxed(barF + 8 * rb, rph, 300);
             else mbar_wait(barF + 8 * rb, rph);
             tc_fence_after();
+            if (mbk == 0) TC_TRACE(a, 1100 + it * NCH + c, 2);
             const uint32_t aU = ring0 + (uint32_t)rb * ringU;
             for (int s = 0; s < spc; ++s) {
               const int taps = min(tps, a.K - s * tps);
@@ -1337,6 +1378,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
               }
           }
           umma_commit_e(leader, BAR_ACCFULL(as));
+          if (mbk == 0) TC_TRACE(a, 3100 + it, 4);
         }
       }
     }
@@ -1356,6 +1398,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
   }
   tc_fence_before();
   __syncthreads();
+  if (warp == 0) TC_TRACE(a, 2, 10);
   if (ncl > 1) cluster_sync_all();     // nobody leaves while a peer may still store into its rings or arrive on its barriers
   if (warp == NW_ACT + 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");

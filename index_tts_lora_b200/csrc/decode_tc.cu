@@ -608,6 +608,9 @@ static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, cons
   // tile after tile (one chunk per tile) and need little weight staging; wide layers walk 6-24 chunks per tile.
   if (!aw) { a.nx = 3; a.nz = 2; a.wst = 4; }                       // plain conv / ConvTranspose1d: the MMA reads the x ring
   else if (cw.Cin <= 96) { a.nx = 3; a.nz = 3; a.wst = 3; }
+  // one column tile (C = 192): the activation warps are the bottleneck and an x tile takes 4-5 kcycles from TMA issue to
+  // arrival under load (pipeline trace, round 2) — longer than one chunk's activation, so two x slots starved them
+  else if (L.n_tiles == 1) { a.nx = 3; a.nz = 3; a.wst = 3; }
   else { a.nx = 2; a.nz = 3; a.wst = 4; }
 #ifdef BVG_EXPERIMENTS
   {
@@ -649,6 +652,7 @@ static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, cons
   const int hc = q.dil * (cw.K - 1) / 2;
   a.lead = q.up ? cw.K - 1 : hc;
   if (aw) {
+    a.xin = static_cast<const __nv_bfloat16*>(q.x); a.xgroups = cw.Cin / 8;   // interior x tiles: 1-D bulk copies
     a.a2 = L.a2; a.nhb = L.nhb;
     for (int i = 0; i < 12; ++i) { a.up2[i] = 2.0f * aw->up[i]; a.dn[i] = aw->dn[i]; }
   }
