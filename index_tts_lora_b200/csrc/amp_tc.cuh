@@ -45,7 +45,7 @@ constexpr int NZ_MAX = 4;     // z ring depth: lets the activation run ahead whi
 constexpr int W_STAGES_MAX = 8;
 constexpr int W_STAGE_BYTES = 16384;
 constexpr int NTHREADS = 768;
-constexpr int MAX_B = 1024;   // utterances per launch (tile-prefix table lives in smem)
+constexpr int MAX_B = 512;    // utterances per launch (tile-prefix table lives in smem; 2 KB — the wide layers use every byte)
 
 constexpr int X_BUF_BYTES = 4 * XRA * 16;  // 22016
 constexpr int X_TX_BYTES = 4 * XR * 16;    // 20480 bytes actually delivered by TMA

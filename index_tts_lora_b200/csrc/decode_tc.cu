@@ -233,6 +233,10 @@ static int pow2_cols(int need) {
 
 static int build_layer(std::vector<void*>& owned, TcLayer& L, const ConvW& cw, const ActW* aw, cudaStream_t st) {
   pick_tile(cw.Cout, &L.n_tile, &L.n_tiles);
+  {
+    static const int split192 = [] { const char* e = getenv("BVG_SPLIT192"); return e ? atoi(e) : 0; }();
+    if (split192 && aw && cw.Cin == 192 && cw.Cout == 192) { L.n_tile = 96; L.n_tiles = 2; }
+  }
   L.nch = (cw.Cin + KC - 1) / KC;
   L.tps = std::max(1, std::min(cw.K, W_STAGE_BYTES / (L.n_tile * 64)));
   L.tmem_cols = pow2_cols(2 * L.n_tile);
@@ -581,6 +585,19 @@ static int launch_act_blk(bvg_plan* p, const ConvW& cw, const ActW* aw, const Tc
   return 0;
 }
 
+#ifdef BVG_EXPERIMENTS
+struct RingOv { int nx = 0, nz = 0, wst = 0; };
+// all three fields must parse and stay inside the mbarrier table; anything else = no override
+static RingOv ring_override(const char* name) {
+  RingOv o;
+  int x = 0, z = 0, w = 0;
+  const char* e = getenv(name);
+  if (e && sscanf(e, "%d,%d,%d", &x, &z, &w) == 3 && x >= 2 && x <= NX_MAX && z >= 2 && z <= NZ_MAX && w >= 2 &&
+      w <= W_STAGES_MAX) { o.nx = x; o.nz = z; o.wst = w; }
+  return o;
+}
+#endif
+
 static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, const ConvW& cw, const ActW* aw,
                      const TcLaunch& q, cudaStream_t st) {
   if (aw && !q.up && q.zbuf && split_layer(cw.Cin)) {
@@ -608,22 +625,21 @@ static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, cons
   // tile after tile (one chunk per tile) and need little weight staging; wide layers walk 6-24 chunks per tile.
   if (!aw) { a.nx = 3; a.nz = 2; a.wst = 4; }                       // plain conv / ConvTranspose1d: the MMA reads the x ring
   else if (cw.Cin <= 96) { a.nx = 3; a.nz = 3; a.wst = 3; }
-  // one column tile (C = 192): the activation warps are the bottleneck and an x tile takes 4-5 kcycles from TMA issue to
-  // arrival under load (pipeline trace, round 2) — longer than one chunk's activation, so two x slots starved them
-  else if (L.n_tiles == 1) { a.nx = 3; a.nz = 3; a.wst = 3; }
-  else { a.nx = 2; a.nz = 3; a.wst = 4; }
+  // wide layers: the weight stream (16 KB per tap, 25-32 B/clk/SM at full MMA rate — most of what L2 can deliver to 148
+  // SMs) is the latency-critical one: 5 stages in flight measured 4.5 % faster than 4, 3 stages 4 % slower, 2 stages 27 %
+  // slower; a third x slot or a fourth z slot bought nothing (per-launch A/B, round 2)
+  else { a.nx = 2; a.nz = 3; a.wst = 5; }
 #ifdef BVG_EXPERIMENTS
   {
-    // BVG_RINGS="nx,nz,wst": ring-depth experiments; all three fields must parse and stay inside the mbarrier table
-    static const std::tuple<int, int, int> ov = [] {
-      int x = 0, z = 0, w = 0;
-      const char* e = getenv("BVG_RINGS");
-      if (!e || sscanf(e, "%d,%d,%d", &x, &z, &w) != 3 || x < 2 || x > NX_MAX || z < 2 || z > NZ_MAX || w < 2 ||
-          w > W_STAGES_MAX)
-        return std::make_tuple(0, 0, 0);
-      return std::make_tuple(x, z, w);
-    }();
-    if (std::get<0>(ov) > 0) { a.nx = std::get<0>(ov); a.nz = std::get<1>(ov); a.wst = std::get<2>(ov); }
+    // ring-depth experiments, "nx,nz,wst": BVG_RINGS (every launch), BVG_RINGS_NARROW (activated, C_in <= 96),
+    // BVG_RINGS_MID (activated, C_in > 96, one column tile), BVG_RINGS_WIDE (activated, several column tiles)
+    static const RingOv ov = ring_override("BVG_RINGS"), ovn = ring_override("BVG_RINGS_NARROW"),
+                        ovm = ring_override("BVG_RINGS_MID"), ovw = ring_override("BVG_RINGS_WIDE");
+    auto apply = [&](const RingOv& o) { if (o.nx > 0) { a.nx = o.nx; a.nz = o.nz; a.wst = o.wst; } };
+    apply(ov);
+    if (aw && cw.Cin <= 96) apply(ovn);
+    if (aw && cw.Cin > 96 && L.n_tiles == 1) apply(ovm);
+    if (aw && L.n_tiles > 1) apply(ovw);
   }
 #endif
   a.Tstride = q.out_tstride ? q.out_tstride : q.Tstride;
