@@ -233,10 +233,6 @@ static int pow2_cols(int need) {
 
 static int build_layer(std::vector<void*>& owned, TcLayer& L, const ConvW& cw, const ActW* aw, cudaStream_t st) {
   pick_tile(cw.Cout, &L.n_tile, &L.n_tiles);
-  {
-    static const int split192 = [] { const char* e = getenv("BVG_SPLIT192"); return e ? atoi(e) : 0; }();
-    if (split192 && aw && cw.Cin == 192 && cw.Cout == 192) { L.n_tile = 96; L.n_tiles = 2; }
-  }
   L.nch = (cw.Cin + KC - 1) / KC;
   L.tps = std::max(1, std::min(cw.K, W_STAGE_BYTES / (L.n_tile * 64)));
   L.tmem_cols = pow2_cols(2 * L.n_tile);
