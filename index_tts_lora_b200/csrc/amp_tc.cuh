@@ -1041,8 +1041,11 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
   }
   if (warp == NW_ACT && lane == 0) {
     // two MMA issuer warps (one per M block): every "the MMAs that read this are done" barrier takes two commits
-    for (int i = 0; i < NX_MAX; ++i) { mbar_init(BAR_XFULL(i), 1); mbar_init(BAR_XEMPTY(i), ACT ? NW_ACT : 2); }
-    for (int i = 0; i < NZ_MAX; ++i) { mbar_init(BAR_ZFULL(i), NW_ACT); mbar_init(BAR_ZEMPTY(i), 2 * ((ACT && a.cl > 1) ? a.cl : 1)); }
+    // activation warps whose channel group lies past C_in in EVERY chunk (C_in < 32: C = 24 -> the 4 warps of group 3)
+    // take no part in the ring hand-shakes at all
+    const int n_act = NW_ACT - 4 * max(0, 4 - (a.Cin >> 3));
+    for (int i = 0; i < NX_MAX; ++i) { mbar_init(BAR_XFULL(i), 1); mbar_init(BAR_XEMPTY(i), ACT ? n_act : 2); }
+    for (int i = 0; i < NZ_MAX; ++i) { mbar_init(BAR_ZFULL(i), ACT ? n_act : NW_ACT); mbar_init(BAR_ZEMPTY(i), 2 * ((ACT && a.cl > 1) ? a.cl : 1)); }
     for (int i = 0; i < 2; ++i) { mbar_init(BAR_ACCFULL(i), 2); mbar_init(BAR_ACCEMPTY(i), 4); }
     for (int i = 0; i < R_RING; ++i) { mbar_init(BAR_RFULL(i), 1); mbar_init(BAR_REMPTY(i), 2); }
     for (int i = 0; i < W_STAGES_MAX; ++i) { mbar_init(BAR_WFULL(i), 1); mbar_init(BAR_WEMPTY(i), 2); }
@@ -1115,13 +1118,19 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
       int xb = 0, xph = 0, zb = 0, zph = 0;     // ring slot / phase of the next chunk
       int b = 0, t0 = 0, nt = 0, T = 0;
       [[maybe_unused]] int trc = 0;
-      if (w0 < total_tiles) {
+      const bool never_live = kg >= live_groups;      // idle in every chunk: not counted by the barriers (see their init)
+      if (live_groups < 4) {
+        // such warps exist (C_in < 32): their zeroed rows above must be visible to the UMMA before the first live arrival
+        if (never_live) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 3, 512;" ::: "memory");      // the 16 activation warps
+      }
+      if (w0 < total_tiles && !never_live) {
         cur.locate(w0, n_tiles, b, t0, nt);
         T = a.lengths ? __ldg(a.lengths + b) * a.rate : a.Tmax;
       }
       float2 a2n = __ldg(reinterpret_cast<const float2*>(a.a2 + (int)crank * KC + kg * 8 + 2 * p));     // my first chunk
       float2 nhbn = __ldg(reinterpret_cast<const float2*>(a.nhb + (int)crank * KC + kg * 8 + 2 * p));
-      for (int w = w0; w < total_tiles; w += wstep) {
+      for (int w = never_live ? total_tiles : w0; w < total_tiles; w += wstep) {
         int b2 = 0, t02 = 0, nt2 = 0, T2 = 0;
         if (w + wstep < total_tiles) {
           cur.locate(w + wstep, n_tiles, b2, t02, nt2);
@@ -1160,8 +1169,8 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
             // before the live warps finish the chunk.  (It used to wait for the x tile and the z slot like a live warp,
             // asleep between polls: every hand-over of a C = 24 / 48 layer then waited for the sleepiest idle warp — the
             // MMA issuer got a chunk 5-9 kcycles after the live warps had finished it, pipeline trace, round 2.)
-            mbar_wait_relaxed(BAR_ZFULL(zb), zph ^ 1, 500);
-            mbar_wait_relaxed(BAR_XEMPTY(xb), xph ^ 1, 500);
+            mbar_wait_relaxed(BAR_ZFULL(zb), zph ^ 1, 1000);     // (nanosleep <= 500 returns at once on this part)
+            mbar_wait_relaxed(BAR_XEMPTY(xb), xph ^ 1, 1000);
           }
           if (warp == 0 && trc < 480) TC_TRACE(a, 600 + trc, 7);
           if (live) {
@@ -1222,7 +1231,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
           cur.locate(w, n_tiles, b, t0, nt);
           for (int c = 0; c < NCH; ++c) {
             if (ncl > 1 && (uint32_t)(c % ncl) != crank) continue;    // that chunk is activated by a peer CTA
-            mbar_wait_relaxed(BAR_XEMPTY(xb), xph ^ 1, 150);
+            mbar_wait_relaxed(BAR_XEMPTY(xb), xph ^ 1, a.Cin <= 96 ? 600u : 150u);
             if (trx < 480) TC_TRACE(a, 2500 + trx, 11);
             ++trx;
             // activated layers never read the channel groups past C_in (their warps skip); plain convs feed the
