@@ -2,7 +2,7 @@
 stream `x = xt + x` either rounded to bf16 after every add (what the kernels do) or kept in fp32 (the bf16
 hi + lo residual).  Prints the waveform SNR against the fp32 oracle.  Result (round 2): an fp32 residual stream buys
 2.2-3.3 dB (tiny stress 38.9 -> 41.1 dB, full stress 42.3 -> 44.5 dB): the bf16 z / weight operands dominate the error, so
-the hi + lo stream was not built.  Usage: python tools/resid_precision_emulation.py   (CPU, ~4 min)"""
+the hi + lo stream was not built.  Usage: python tests/resid_precision_emulation.py   (CPU, ~4 min)"""
 import os, sys, torch, torch.nn.functional as F
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import warnings; warnings.filterwarnings("ignore")
