@@ -114,8 +114,9 @@ int bvg_decode(bvg_plan* plan, const void* latent, int latent_dtype, const int32
                int B, int Tmax, const float* spk_emb, void* wav_out, int wav_dtype,
                int precision, void* stream);
 
-/* Same, with HOST buffers for the bulk data (pinned for async copies): H2D of the latent,
- * decode, D2H of wav, then synchronises `stream`.  `spk_emb` stays a DEVICE pointer (the ECAPA
+/* Same, with HOST buffers for the bulk data (pinned for async copies): H2D of the latent (on a copy
+ * stream owned by the plan, so that it runs beside work already queued on `stream`, e.g. the speaker
+ * encoder of the same request; the decode waits for it by event), decode, D2H of wav, then synchronises `stream`.  `spk_emb` stays a DEVICE pointer (the ECAPA
  * encoder runs on the device).  This is the end-to-end call bench.py times as `e2e`. */
 int bvg_decode_host(bvg_plan* plan, const void* latent_host, int latent_dtype,
                     const int32_t* lengths, int B, int Tmax, const float* spk_emb,

@@ -532,6 +532,8 @@ int bvg_plan_destroy(bvg_plan* p) {
   for (const ProfRec& r : p->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
   if (p->st_lat) cudaFree(p->st_lat);
+  if (p->ev_h2d) cudaEventDestroy(p->ev_h2d);
+  if (p->copy_st) cudaStreamDestroy(p->copy_st);
   if (p->st_emb) cudaFree(p->st_emb);
   if (p->st_wav) cudaFree(p->st_wav);
   tc_plan_free(p);
@@ -650,7 +652,17 @@ int bvg_decode_host(bvg_plan* p, const void* latent_host, int latent_dtype, cons
   int rc;
   if ((rc = grow(&p->st_lat, &p->st_lat_bytes, lat_bytes))) return rc;
   if ((rc = grow(&p->st_wav, &p->st_wav_bytes, wav_bytes))) return rc;
-  BVG_CUDA(cudaMemcpyAsync(p->st_lat, latent_host, lat_bytes, cudaMemcpyHostToDevice, st));
+  // The latents go up on the plan's own copy stream, beside whatever the caller has already queued on `st` — in
+  // infer.py's order that is the speaker encoder of the same request (models.py:204), whose output `spk_emb` this
+  // call consumes — and the decode waits for the copy by event.  The staging buffer is free: the previous call on this
+  // plan ended with a stream synchronize.
+  if (!p->copy_st) {
+    BVG_CUDA(cudaStreamCreateWithFlags(&p->copy_st, cudaStreamNonBlocking));
+    BVG_CUDA(cudaEventCreateWithFlags(&p->ev_h2d, cudaEventDisableTiming));
+  }
+  BVG_CUDA(cudaMemcpyAsync(p->st_lat, latent_host, lat_bytes, cudaMemcpyHostToDevice, p->copy_st));
+  BVG_CUDA(cudaEventRecord(p->ev_h2d, p->copy_st));
+  BVG_CUDA(cudaStreamWaitEvent(st, p->ev_h2d, 0));
   if ((rc = bvg_decode(p, p->st_lat, latent_dtype, lengths, B, Tmax, spk_emb, p->st_wav, wav_dtype,
                        precision, stream)))
     return rc;

@@ -68,6 +68,8 @@ struct bvg_plan {
   int len_slot = 0;
   // host-variant staging
   void* st_lat = nullptr;  size_t st_lat_bytes = 0;
+  cudaStream_t copy_st = nullptr;       // bvg_decode_host: the H2D of the latents runs beside the caller's queued work
+  cudaEvent_t ev_h2d = nullptr;
   float* st_emb = nullptr; size_t st_emb_elems = 0;
   void* st_wav = nullptr;  size_t st_wav_bytes = 0;
 
