@@ -1266,6 +1266,9 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
       // staged by TMA in the UMMA A layout; I = identity weight tile streamed through the weight ring like a tap.
       if (lane == 0) {
         int stage = 0, phase = 0, rs = 0, rph = 0;
+        // narrow layers: a tile's worth of slack on every ring, and whatever this thread executes while waiting comes out of
+        // the activation warps' issue slots — sleep for real (nanosleep <= 500 returns at once on this part)
+        const uint32_t nap = a.Cin <= 96 ? 800u : 300u;
         TileCursor cur{prefix};
         for (int w = w0; w < total_tiles; w += wstep) {
           int b, t0, nt;
@@ -1275,7 +1278,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
             for (int s = 0; s < spc; ++s) {
               const int taps = min(tps, a.K - s * tps);
               const uint32_t bytes = BVG_DBGBIT(a, 2) ? 16u : (uint32_t)(taps * tile_bytes);
-              mbar_wait_relaxed(BAR_WEMPTY(stage), phase ^ 1, 300);
+              mbar_wait_relaxed(BAR_WEMPTY(stage), phase ^ 1, nap);
               mbar_expect_tx(BAR_WFULL(stage), bytes);
               bulk_load(s_base + OFF_W + stage * W_STAGE_BYTES, src, bytes, BAR_WFULL(stage));
               src += bytes;
@@ -1288,11 +1291,11 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
                 const CUtensorMap* rm = (st == 0 && a.rmma_r) ? &tmr : &tmq;
                 // identity tile of (column tile nt, input chunk nt * nchr + c)
                 const uint8_t* isrc = reinterpret_cast<const uint8_t*>(a.idw) + ((size_t)nt * NCH + nt * a.nchr + c) * tile_bytes;
-                mbar_wait_relaxed(BAR_WEMPTY(stage), phase ^ 1, 300);
+                mbar_wait_relaxed(BAR_WEMPTY(stage), phase ^ 1, nap);
                 mbar_expect_tx(BAR_WFULL(stage), (uint32_t)tile_bytes);
                 bulk_load(s_base + OFF_W + stage * W_STAGE_BYTES, isrc, (uint32_t)tile_bytes, BAR_WFULL(stage));
                 if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
-                mbar_wait_relaxed(BAR_REMPTY(rs), rph ^ 1, 300);
+                mbar_wait_relaxed(BAR_REMPTY(rs), rph ^ 1, nap);
                 mbar_expect_tx(BAR_RFULL(rs), R_SLOT_BYTES);
                 const uint32_t dst = s_base + OFF_R + rs * R_SLOT_BYTES;
                 const int g0 = nt * (n_tile >> 3) + c * 4;
@@ -1346,7 +1349,7 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
           for (int c = 0; c < NCH; ++c) {
             // narrow layers are bound by the activation warps' issue slots: the issuer sleeps between polls there
             if (ncl > 1) mbar_wait_acq_cluster(barF + 8 * rb, rph);     // arrivals (and bulk-copy bytes) come from peer CTAs too
-            else if (lazy) mbar_wait_relaxed(barF + 8 * rb, rph, 300);
+            else if (lazy) mbar_wait_relaxed(barF + 8 * rb, rph, 800);
             else mbar_wait(barF + 8 * rb, rph);
             tc_fence_after();
             if (mbk == 0) TC_TRACE(a, 1100 + it * NCH + c, 2);
