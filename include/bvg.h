@@ -109,6 +109,8 @@ int bvg_plan_load_weights(bvg_plan* plan, const bvg_tensor_desc* tensors, int n,
  *   wav_out  device, [B, 1, Tmax * prod(upsample_rates)], dtype wav_dtype:
  *            F32/BF16/F16 = tanh output (models.py:250);  I16 = clamp(32767*wav) as in
  *            infer.py:892.  Samples beyond an utterance's length are written as 0.
+ * The bf16 (tcgen05) path takes at most 512 utterances per call (the per-launch tile table lives in shared
+ * memory); more returns BVG_ERR_UNSUPPORTED — split the batch.
  */
 int bvg_decode(bvg_plan* plan, const void* latent, int latent_dtype, const int32_t* lengths,
                int B, int Tmax, const float* spk_emb, void* wav_out, int wav_dtype,
