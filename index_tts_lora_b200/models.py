@@ -409,6 +409,8 @@ class BigVGAN(nn.Module):
         g.replay()
         return static_out.clone()
 
+    MAX_UTTERANCES_PER_CALL = 512
+
     def decode(self, x: torch.Tensor, speaker_embedding: torch.Tensor,
                lengths: Optional[Sequence[int]] = None, out_dtype=None) -> torch.Tensor:
         """models.py:212-252 on the GPU.  x [B,T,gpt_dim]; speaker_embedding [B|1,1,D] or [B|1,D];
@@ -432,16 +434,19 @@ class BigVGAN(nn.Module):
             out_dtype = x.dtype if x.dtype in (torch.float32, torch.bfloat16, torch.float16) \
                 else torch.float32
         wav = torch.empty(B, 1, T * up, device=x.device, dtype=out_dtype)
-        lens_arr = None
-        if lengths is not None:
-            if len(lengths) != B:
-                raise ValueError("lengths must have one entry per utterance")
-            lens_arr = (C.c_int32 * B)(*[int(v) for v in lengths])
+        if lengths is not None and len(lengths) != B:
+            raise ValueError("lengths must have one entry per utterance")
+        # one native call takes at most MAX_UTTERANCES_PER_CALL utterances (include/bvg.h): larger batches go in slices
         with torch.cuda.device(x.device):
-            _lib.check(lib.bvg_decode(plan, x.data_ptr(), _lib.torch_dtype_code(x.dtype), lens_arr,
-                                      B, T, emb.data_ptr(), wav.data_ptr(),
-                                      _lib.torch_dtype_code(out_dtype), self._precision_code(),
-                                      _lib.stream_ptr(x.device)), "bvg_decode")
+            for b0 in range(0, B, self.MAX_UTTERANCES_PER_CALL):
+                nb = min(self.MAX_UTTERANCES_PER_CALL, B - b0)
+                lens_arr = None
+                if lengths is not None:
+                    lens_arr = (C.c_int32 * nb)(*[int(v) for v in lengths[b0:b0 + nb]])
+                _lib.check(lib.bvg_decode(plan, x[b0:b0 + nb].data_ptr(), _lib.torch_dtype_code(x.dtype), lens_arr,
+                                          nb, T, emb[b0:b0 + nb].data_ptr(), wav[b0:b0 + nb].data_ptr(),
+                                          _lib.torch_dtype_code(out_dtype), self._precision_code(),
+                                          _lib.stream_ptr(x.device)), "bvg_decode")
         return wav
 
     def forward(self, x, mel_ref, lens=None):

@@ -717,3 +717,30 @@ def test_ragged_batch_bf16_cluster_equals_plain():
     for b, L in enumerate(lengths):
         if L < max(lengths):
             assert y1[b, :, L * 1024:].abs().max().item() == 0.0
+
+
+@pytest.mark.gpu
+def test_decode_slices_batches_beyond_the_native_limit():
+    """BigVGAN.decode feeds the native call at most MAX_UTTERANCES_PER_CALL utterances at a time (the tile table of one
+    launch holds 512): a batch beyond the limit must equal the same utterances decoded in two calls."""
+    from index_tts_lora_b200.config import tiny_config
+    from index_tts_lora_b200 import synth
+    from index_tts_lora_b200.models import BigVGAN
+    dev = _dev()
+    h = tiny_config()
+    m = BigVGAN(h)
+    m.load_state_dict(synth.synth_state_dict(m.state_dict(), seed=1234, profile="init"))
+    m = m.to(dev).eval()
+    m.precision = "bf16"
+    B, F_ = 7, 9
+    lat = synth.synth_latent(B, F_, h.gpt_dim, seed=5).to(dev)
+    emb = torch.randn(B, h.speaker_embedding_dim, generator=synth._gen(7, "emb")).to(dev) * 0.1
+    lengths = [9, 3, 9, 1, 5, 9, 2]
+    whole = m.decode(lat, emb, lengths=lengths, out_dtype=torch.float32).cpu()
+    old = BigVGAN.MAX_UTTERANCES_PER_CALL
+    try:
+        BigVGAN.MAX_UTTERANCES_PER_CALL = 3
+        sliced = m.decode(lat, emb, lengths=lengths, out_dtype=torch.float32).cpu()
+    finally:
+        BigVGAN.MAX_UTTERANCES_PER_CALL = old
+    assert torch.equal(whole, sliced)
