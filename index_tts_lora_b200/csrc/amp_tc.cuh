@@ -1117,7 +1117,6 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
       TileCursor cur{prefix};
       int xb = 0, xph = 0, zb = 0, zph = 0;     // ring slot / phase of the next chunk
       int b = 0, t0 = 0, nt = 0, T = 0;
-      [[maybe_unused]] int trc = 0;
       const bool never_live = kg >= live_groups;      // idle in every chunk: not counted by the barriers (see their init)
       if (live_groups < 4) {
         // such warps exist (C_in < 32): their zeroed rows above must be visible to the UMMA before the first live arrival
@@ -1161,7 +1160,6 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
           const bool live = vlo < ZW && c * 4 + kg < live_groups;
           if (live) {
             mbar_wait(BAR_XFULL(xb), xph);
-            if (warp == 0 && trc < 480) TC_TRACE(a, 2000 + trc, 8);
             mbar_wait(BAR_ZEMPTY(zb), zph ^ 1);
           } else {
             // Nothing to read or write: this warp only owes the two barriers its arrival, and it pays EARLY — as soon as
@@ -1172,7 +1170,6 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
             mbar_wait_relaxed(BAR_ZFULL(zb), zph ^ 1, 1000);     // (nanosleep <= 500 returns at once on this part)
             mbar_wait_relaxed(BAR_XEMPTY(xb), xph ^ 1, 1000);
           }
-          if (warp == 0 && trc < 480) TC_TRACE(a, 600 + trc, 7);
           if (live) {
             const uint32_t* xk = reinterpret_cast<const uint32_t*>(smem + OFF_X + xb * X_BUF_BYTES) + kg * (XRA * 4) + p;
             uint32_t* zk = reinterpret_cast<uint32_t*>(smem + OFF_Z + zb * Z_BUF_BYTES) + kg * (ZR * 4) + p;
@@ -1211,7 +1208,6 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
             }
             mbar_arrive(BAR_XEMPTY(xb));
           }
-          if (warp == 0) { if (trc < 480) TC_TRACE(a, 100 + trc, 1); ++trc; }
           if (++xb == NX) { xb = 0; xph ^= 1; }
           if (++zb == NZ) { zb = 0; zph ^= 1; }
         }

@@ -19,8 +19,8 @@ if os.environ.get("TC_TRACE_CHILD") != "1":
     for it in range(8):
         if 3000 + it not in ev: break
         print(f"tile {it}: mma start {k(3000+it):8.1f}  mma issued {k(3100+it):8.1f}  epi start {k(3200+it):8.1f}  epi end {k(3300+it):8.1f}")
-    print("own chunks (activation warp 0): x tile there / z slot free (start) - done   [x load issued]")
-    print("  ".join(f"{i}:{k(2000+i):.1f}/{k(600+i):.1f}-{k(100+i):.1f}[{k(2500+i):.1f}]" for i in range(480) if 100 + i in ev and i < 40))
+    print("x loads issued (chunk sequence of this CTA; no stamps inside the activation warps: they cost the narrow layers 16 %):")
+    print("  ".join(f"{i}:{k(2500+i):.1f}" for i in range(480) if 2500 + i in ev and i < 60))
     print("MMA issuer got chunk (tile*NCH + c):")
     print("  ".join(f"{i}:{k(1100+i):.1f}" for i in range(1900) if 1100 + i in ev and i < 80))
     sys.exit(0)
