@@ -1072,6 +1072,48 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
   pdl_wait();          // the prologue above only read launch constants (lengths, parameters); activations from here on
   if (warp == 0) TC_TRACE(a, 1, 9);
 
+  // The x producer's loop: channel groups [g_lo, g_hi) of every chunk; `lead` announces the bytes.  Activated layers run
+  // it from ONE thread (groups 0-3).  Un-activated layers (conv_pre, ConvTranspose1d) feed the MMAs straight from the x
+  // ring and their 16 activation warps have nothing to do, so three of them take a channel group each beside the
+  // producer warp: one thread gets a copy out every ~0.3 us whatever the ring depth, and copies from different WARPS
+  // proceed in parallel (tools/bulk_probe.cu) — the narrow ConvTranspose1d launches were bound by exactly that rate.
+  auto x_loop = [&](const int g_lo, const int g_hi, const bool lead) {
+        TileCursor cur{prefix};
+        int xb = 0, xph = 0;
+        [[maybe_unused]] int trx = 0;
+        for (int w = w0; w < total_tiles; w += wstep) {
+          int b, t0, nt;
+          cur.locate(w, n_tiles, b, t0, nt);
+          for (int c = 0; c < NCH; ++c) {
+            if (ncl > 1 && (uint32_t)(c % ncl) != crank) continue;    // that chunk is activated by a peer CTA
+            mbar_wait_relaxed(BAR_XEMPTY(xb), xph ^ 1, a.Cin <= 96 ? 600u : 150u);
+            if (lead && trx < 480) TC_TRACE(a, 2500 + trx, 11);
+            ++trx;
+            // activated layers never read the channel groups past C_in (their warps skip); plain convs feed the
+            // x tile to the MMA as it is and need the TMA zero fill of those groups
+            const int lg = ACT ? min(4, (a.Cin >> 3) - c * 4) : 4;
+            if (lead) mbar_expect_tx(BAR_XFULL(xb), (uint32_t)lg * (X_TX_BYTES / 4));
+            const uint32_t dst = s_base + OFF_X + xb * X_BUF_BYTES;
+            // The XR rows of one (utterance, channel group) are contiguous in the blocked layout: a tile whose window lies
+            // inside the buffer takes one 1-D bulk copy per group (5 KB) instead of two tensor boxes, which the TMA unit
+            // walks 16-byte row by row (~1 row / clk).  Windows that leave [0, Tmax) keep the tensor path for its zero fill.
+            if (a.xin && t0 - X_LEAD >= 0 && t0 - X_LEAD + XR <= a.Tmax && (ACT || c * 4 + 4 <= a.xgroups)) {
+              const __nv_bfloat16* src = a.xin + (((size_t)b * a.xgroups + c * 4) * a.Tmax + (t0 - X_LEAD)) * 8;
+#pragma unroll
+              for (int kg = 0; kg < 4; ++kg)
+                if (kg < lg && kg >= g_lo && kg < g_hi) bulk_load(dst + kg * (XRA * 16), src + (size_t)kg * a.Tmax * 8, XR * 16, BAR_XFULL(xb));
+            } else {
+#pragma unroll
+              for (int kg = 0; kg < 4; ++kg)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                  if (kg < lg && kg >= g_lo && kg < g_hi) tma_load_4d(dst + kg * (XRA * 16) + h * (BOXR * 16), &tmx, 0, t0 - X_LEAD + h * BOXR, c * 4 + kg, b,
+                              BAR_XFULL(xb));
+            }
+            if (++xb == NX) { xb = 0; xph ^= 1; }
+          }
+        }
+  };
   if (warp < NW_ACT) {
     // ===================== activation warps =====================
     reg_inc<96>();
@@ -1213,48 +1255,14 @@ k_amp_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtens
         }
         b = b2; t0 = t02; nt = nt2; T = T2;
       }
+    } else if (warp >= 1 && warp < 4 && lane == 0) {
+      x_loop(warp, warp + 1, false);          // un-activated layer: channel group `warp` of every x tile
     }
   } else if (warp < NW_ACT + 4) {
     reg_dec<32>();
     if (warp == NW_ACT) {
       // ===================== x producer (TMA) =====================
-      if (lane == 0) {
-        TileCursor cur{prefix};
-        int xb = 0, xph = 0;
-        [[maybe_unused]] int trx = 0;
-        for (int w = w0; w < total_tiles; w += wstep) {
-          int b, t0, nt;
-          cur.locate(w, n_tiles, b, t0, nt);
-          for (int c = 0; c < NCH; ++c) {
-            if (ncl > 1 && (uint32_t)(c % ncl) != crank) continue;    // that chunk is activated by a peer CTA
-            mbar_wait_relaxed(BAR_XEMPTY(xb), xph ^ 1, a.Cin <= 96 ? 600u : 150u);
-            if (trx < 480) TC_TRACE(a, 2500 + trx, 11);
-            ++trx;
-            // activated layers never read the channel groups past C_in (their warps skip); plain convs feed the
-            // x tile to the MMA as it is and need the TMA zero fill of those groups
-            const int lg = ACT ? min(4, (a.Cin >> 3) - c * 4) : 4;
-            mbar_expect_tx(BAR_XFULL(xb), (uint32_t)lg * (X_TX_BYTES / 4));
-            const uint32_t dst = s_base + OFF_X + xb * X_BUF_BYTES;
-            // The XR rows of one (utterance, channel group) are contiguous in the blocked layout: a tile whose window lies
-            // inside the buffer takes one 1-D bulk copy per group (5 KB) instead of two tensor boxes, which the TMA unit
-            // walks 16-byte row by row (~1 row / clk).  Windows that leave [0, Tmax) keep the tensor path for its zero fill.
-            if (ACT && a.xin && t0 - X_LEAD >= 0 && t0 - X_LEAD + XR <= a.Tmax) {
-              const __nv_bfloat16* src = a.xin + (((size_t)b * a.xgroups + c * 4) * a.Tmax + (t0 - X_LEAD)) * 8;
-#pragma unroll
-              for (int kg = 0; kg < 4; ++kg)
-                if (kg < lg) bulk_load(dst + kg * (XRA * 16), src + (size_t)kg * a.Tmax * 8, XR * 16, BAR_XFULL(xb));
-            } else {
-#pragma unroll
-              for (int kg = 0; kg < 4; ++kg)
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-                  if (kg < lg) tma_load_4d(dst + kg * (XRA * 16) + h * (BOXR * 16), &tmx, 0, t0 - X_LEAD + h * BOXR, c * 4 + kg, b,
-                              BAR_XFULL(xb));
-            }
-            if (++xb == NX) { xb = 0; xph ^= 1; }
-          }
-        }
-      }
+      if (lane == 0) x_loop(0, ACT ? 4 : 1, true);
     } else if (warp == NW_ACT + 1) {
       // ===================== weight producer (bulk copies) =====================
       // ... and the residual / running-sum rows of the tile: the layer's `+ x` (models.py:72) and the sum over the three

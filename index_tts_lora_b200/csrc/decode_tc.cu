@@ -663,8 +663,8 @@ static int launch_tc(bvg_plan* p, const CUtensorMap& map, const TcLayer& L, cons
 #endif
   const int hc = q.dil * (cw.K - 1) / 2;
   a.lead = q.up ? cw.K - 1 : hc;
+  a.xin = static_cast<const __nv_bfloat16*>(q.x); a.xgroups = cw.Cin / 8;   // interior x tiles: 1-D bulk copies
   if (aw) {
-    a.xin = static_cast<const __nv_bfloat16*>(q.x); a.xgroups = cw.Cin / 8;   // interior x tiles: 1-D bulk copies
     a.a2 = L.a2; a.nhb = L.nhb;
     for (int i = 0; i < 12; ++i) { a.up2[i] = 2.0f * aw->up[i]; a.dn[i] = aw->dn[i]; }
   }
