@@ -169,6 +169,62 @@ __global__ void __launch_bounds__(256) k_conv_post_blk(const __nv_bfloat16* __re
   st_dyn(out, (size_t)b * Tstride + t, out_dtype, acc);
 }
 
+// The same for K = 7 (config.yaml's conv_post), four consecutive outputs per thread: the 10 x C/8 rows they need are
+// loaded once (16-byte loads, 7.5 per output instead of 21) and every tap weight read from shared memory serves four
+// FMAs — the one-output form issues one LDS per FMA and is bound by exactly that (154 us for 16 x 10 s).
+template <int K>
+__global__ void __launch_bounds__(256) k_conv_post_blk4(const __nv_bfloat16* __restrict__ z, const float* __restrict__ wp,
+                                                        const float* __restrict__ bias, void* __restrict__ out, int out_dtype,
+                                                        int groups, int Tstride, const int* __restrict__ lengths, int rate) {
+  __shared__ float ws[8 * 16 * K];                  // [C][K] tap weights, C <= 128
+  pdl_launch_dependents();
+  const int C = groups * 8;
+  for (int i = threadIdx.x; i < C * K; i += blockDim.x) ws[i] = wp[i];   // wp is [Cin][K][Cout = 1]
+  __syncthreads();
+  pdl_wait();
+  constexpr int NT = 4, hk = (K - 1) / 2, NR = NT + K - 1;
+  const int b = blockIdx.y;
+  const int t0 = (blockIdx.x * blockDim.x + threadIdx.x) * NT;
+  if (t0 >= Tstride) return;
+  const int T = lengths ? lengths[b] * rate : Tstride;
+  float acc[NT];
+  const float b0 = bias[0];
+#pragma unroll
+  for (int o = 0; o < NT; ++o) acc[o] = b0;
+  if (t0 < T) {
+    for (int g = 0; g < groups; ++g) {
+      uint4 rows[NR];
+      const __nv_bfloat16* zg = z + ((size_t)b * groups + g) * Tstride * 8;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const int tt = t0 + r - hk;
+        rows[r] = (tt >= 0 && tt < T) ? __ldg(reinterpret_cast<const uint4*>(zg + (size_t)tt * 8)) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          const float w = ws[(g * 8 + e) * K + j];
+#pragma unroll
+          for (int o = 0; o < NT; ++o) {
+            const uint4& rw = rows[o + j];
+            const uint32_t wd = (e >> 1) == 0 ? rw.x : (e >> 1) == 1 ? rw.y : (e >> 1) == 2 ? rw.z : rw.w;
+            acc[o] = fmaf(w, __uint_as_float((e & 1) ? (wd & 0xffff0000u) : (wd << 16)), acc[o]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < NT; ++o) {
+    const int t = t0 + o;
+    if (t >= Tstride) break;
+    float v = 0.f;
+    if (t < T) asm("tanh.approx.f32 %0, %1;" : "=f"(v) : "f"(acc[o]));
+    st_dyn(out, (size_t)b * Tstride + t, out_dtype, v);
+  }
+}
+
 // ------------------------------------------------------------------------------ plan state
 struct TcLayer {
   __nv_bfloat16* wt = nullptr;
@@ -973,8 +1029,14 @@ static int tc_post(bvg_plan* p, TcPlan* t, const __nv_bfloat16* cur, void* wav_o
   if (!(parts & 2)) return 0;
   dim3 gridp(ceil_div(Ts, 256), B);
   prof_begin(p, st, 3, 2.0 * Cp * Kp * p->cur_sum_frames * p->rate[S], (2.0 * Cp + 4.0) * p->cur_sum_frames * p->rate[S]);
-  BVG_CUDA(launch_k(k_conv_post_blk, gridp, dim3(256), 0, st, true, (const __nv_bfloat16*)zpost, (const float*)p->conv_post.wp,
-                    (const float*)p->conv_post.bias, wav_out, wav_dtype, Cp / 8, Kp, Ts, d_len, p->rate[S]));
+  if (Kp == 7) {
+    dim3 grid4(ceil_div(Ts, 256 * 4), B);
+    BVG_CUDA(launch_k(k_conv_post_blk4<7>, grid4, dim3(256), 0, st, true, (const __nv_bfloat16*)zpost, (const float*)p->conv_post.wp,
+                      (const float*)p->conv_post.bias, wav_out, wav_dtype, Cp / 8, Ts, d_len, p->rate[S]));
+  } else {
+    BVG_CUDA(launch_k(k_conv_post_blk, gridp, dim3(256), 0, st, true, (const __nv_bfloat16*)zpost, (const float*)p->conv_post.wp,
+                      (const float*)p->conv_post.bias, wav_out, wav_dtype, Cp / 8, Kp, Ts, d_len, p->rate[S]));
+  }
   prof_end(p, st);
   BVG_CUDA(cudaGetLastError());
   ++p->last_launches;
